@@ -1,0 +1,143 @@
+"""ORACLE (test infrastructure, not product code): the reference's CPU algorithm for the backbone, restated.
+
+Sparse convolution in MinkowskiEngine's own CPU formulation -- per kernel offset: gather rows, GEMM,
+scatter-add (SURVEY 2.4 / 8d "CPU baseline") -- with torch CPU tensors so that autograd provides the backward
+pass, wired into the ResUNet exactly as the reference wires it:
+
+  torch_points3d/modules/MinkowskiEngine/api_modules.py:26-82   ResBlock (conv3 BN ReLU conv3 BN ReLU + shortcut)
+  torch_points3d/modules/MinkowskiEngine/api_modules.py:251-285 ResNetDown (conv_in BN ReLU, N blocks)
+  torch_points3d/modules/MinkowskiEngine/api_modules.py:288-311 ResNetUp (cat skip, transposed convs)
+  torch_points3d/applications/minkowski.py:160-196              MinkowskiUnet.forward (skip stack)
+  torch_points3d/models/panoptic/PointGroup3heads.py:69-81,103-108 heads
+
+It is written functionally over a state_dict (no nn.Module shared with the product) so that the wiring is an
+independent restatement.  PARITY UNPINNED against MinkowskiEngine itself (absent, see sparse_ref.py header).
+
+Used by: tests/ (parity of the CUDA path), __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import sparse_ref as sr
+
+
+class CpuMaps(sr.Maps):
+    """sparse_ref.Maps + cached torch pair lists per kernel map."""
+
+    def __init__(self, coords):
+        super().__init__(coords)
+        self._pairs = {}
+
+    def pair_lists(self, nbr):
+        key = id(nbr)
+        if key not in self._pairs:
+            i, o, offs = sr.pairs(nbr)
+            self._pairs[key] = (torch.from_numpy(i.astype(np.int64)), torch.from_numpy(o.astype(np.int64)),
+                                offs.tolist(), nbr)
+        return self._pairs[key]
+
+
+def sparse_conv(X, W, maps, ts, ksize, stride, transpose):
+    """-> (Y, ts_out).  Per-offset gather -> mm -> index_add_ (autograd-able)."""
+    nbr, mirror, _, _, ts_out = maps.conv_maps(ts, ksize, stride, transpose)
+    if nbr is None:
+        return X @ W.reshape(W.shape[-2], W.shape[-1]), ts_out
+    in_idx, out_idx, offs, _ = maps.pair_lists(nbr)
+    K = W.shape[0]
+    Y = torch.zeros(nbr.shape[1], W.shape[2], dtype=X.dtype)
+    for tk in range(K):
+        a, b = offs[tk], offs[tk + 1]
+        if b > a:
+            k = K - 1 - tk if mirror else tk
+            Y = Y.index_add(0, out_idx[a:b], X.index_select(0, in_idx[a:b]) @ W[k])
+    return Y, ts_out
+
+
+def _bn(x, sd, prefix, training, eps=1e-5):
+    if training:
+        return F.batch_norm(x, None, None, sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"], True, 0.0, eps)
+    return F.batch_norm(x, sd[prefix + ".bn.running_mean"], sd[prefix + ".bn.running_var"],
+                        sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"], False, 0.0, eps)
+
+
+def _res_block(x, ts, sd, p, maps, transpose, training):
+    y, _ = sparse_conv(x, sd[p + ".block.0.kernel"], maps, ts, 3, 1, transpose)
+    y = torch.relu(_bn(y, sd, p + ".block.1", training))
+    y, _ = sparse_conv(y, sd[p + ".block.3.kernel"], maps, ts, 3, 1, transpose)
+    y = torch.relu(_bn(y, sd, p + ".block.4", training))
+    if (p + ".downsample.0.kernel") in sd:
+        s, _ = sparse_conv(x, sd[p + ".downsample.0.kernel"], maps, ts, 1, 1, transpose)
+        s = _bn(s, sd, p + ".downsample.1", training)
+    else:
+        s = x
+    return y + s
+
+
+def _res_level(x, ts, sd, p, maps, ksize, stride, n_blocks, transpose, training):
+    y, ts = sparse_conv(x, sd[p + ".conv_in.0.kernel"], maps, ts, ksize, stride, transpose)
+    y = torch.relu(_bn(y, sd, p + ".conv_in.1", training))
+    for j in range(n_blocks):
+        y = _res_block(y, ts, sd, "%s.blocks.%d" % (p, j), maps, transpose, training)
+    return y, ts
+
+
+def _per_level(v, i):
+    return v[i] if isinstance(v, (list, tuple)) else v
+
+
+def unet_forward(sd, cfg, x, coords, training=True, prefix=""):
+    """MinkowskiUnet.forward over a state_dict.  cfg = resolved compact config (ints).  -> [N, C_out]."""
+    maps = CpuMaps(np.asarray(coords))
+    down, up = cfg["down_conv"], cfg["up_conv"]
+    nd, nu = len(down["down_conv_nn"]), len(up["up_conv_nn"])
+    ts = 1
+    stack = []
+    for i in range(nd):
+        x, ts = _res_level(x, ts, sd, "%sdown_modules.%d" % (prefix, i), maps, _per_level(down["kernel_size"], i),
+                           _per_level(down["stride"], i), _per_level(down["N"], i), False, training)
+        stack.append((x, ts) if i < nd - 1 else None)
+    for i in range(nu):
+        skip = stack.pop()
+        if skip is not None:
+            assert skip[1] == ts
+            x = torch.cat([x, skip[0]], dim=1)
+        x, ts = _res_level(x, ts, sd, "%sup_modules.%d" % (prefix, i), maps, _per_level(up["kernel_size"], i),
+                           _per_level(up["stride"], i), _per_level(up["N"], i), True, training)
+    assert ts == 1
+    return x
+
+
+def mlp_head(x, sd, p, training, final_bias=True):
+    """Seq(MLP([C,C], bias=False), Linear) with FastBatchNorm1d + LeakyReLU(0.2)
+    (core/common_modules/base_modules.py:35-45; PointGroup3heads.py:69-81)."""
+    y = x @ sd[p + ".0.0.0.weight"].t()
+    bnp = p + ".0.0.1.batch_norm"
+    if training:
+        y = F.batch_norm(y, None, None, sd[bnp + ".weight"], sd[bnp + ".bias"], True, 0.0, 1e-5)
+    else:
+        y = F.batch_norm(y, sd[bnp + ".running_mean"], sd[bnp + ".running_var"], sd[bnp + ".weight"],
+                         sd[bnp + ".bias"], False, 0.0, 1e-5)
+    y = F.leaky_relu(y, 0.2)
+    return y @ sd[p + ".1.weight"].t() + sd[p + ".1.bias"]
+
+
+def resolve_cfg(cfg, input_nc):
+    """Evaluate the "2*in_feat" style strings (model_definition_resolver.py:29-58)."""
+    consts = {"FEAT": input_nc}
+    for k, v in (cfg.get("define_constants") or {}).items():
+        consts[k] = eval(v, {}, consts) if isinstance(v, str) else v
+
+    def ev(o):
+        if isinstance(o, str):
+            try:
+                return eval(o, {"__builtins__": {}}, consts)
+            except Exception:
+                return o
+        if isinstance(o, (list, tuple)):
+            return [ev(v) for v in o]
+        if isinstance(o, dict):
+            return {k: ev(v) for k, v in o.items()}
+        return o
+
+    return ev(cfg)

@@ -1,0 +1,93 @@
+"""ctypes binding of libpgs_b200.so (the C ABI declared in include/pgs_b200.h).
+
+There is no CPU fallback: every op in this package goes through this library, and the library
+only holds sm_100a device code.  If the shared object is missing (and cannot be built) the
+import of the op fails loudly.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_size_t, c_void_p, c_char_p, c_float, c_double
+
+import torch
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# name -> (restype, argtypes); kept in one place so tests can check it against the header
+SIGNATURES = {
+    "pgs_version": (c_int, []),
+    "pgs_last_error": (c_char_p, []),
+    "pgs_launch_count": (c_int64, []),
+    "pgs_cmap_capacity": (c_int64, [c_int64]),
+    "pgs_cmap_build_scratch_bytes": (c_size_t, [c_int64]),
+    "pgs_cmap_build": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pgs_kmap_build": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                               c_void_p, c_void_p]),
+    "pgs_kmap_pairs_scratch_bytes": (c_size_t, [c_int64, c_int32]),
+    "pgs_kmap_pairs": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                               c_void_p]),
+    "pgs_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+                             c_int32, c_void_p, c_void_p]),
+    "pgs_conv_bwd_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                    c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+}
+
+
+class PgsError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if sources are newer and nvcc exists) and return the ctypes handle."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if os.path.exists(_build.NVCC):
+        try:
+            _build.build()
+        except Exception as e:  # pragma: no cover - build errors must be visible
+            raise PgsError("building libpgs_b200.so failed: %s" % e)
+    if not os.path.exists(path):
+        raise PgsError(
+            "libpgs_b200.so not found at %s and nvcc is unavailable: the B200 CUDA extension is required "
+            "(there is no CPU fallback). Run `python -m panopticsegforlargescalepointcloud_b200.build`." % path
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PgsError(load().pgs_last_error().decode())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise PgsError("expected a CUDA tensor: the B200 path has no CPU implementation")
+    if not t.is_contiguous():
+        raise PgsError("expected a contiguous tensor")
+    return c_void_p(t.data_ptr())
+
+
+def launch_count():
+    return int(load().pgs_launch_count())

@@ -1,0 +1,469 @@
+"""MinkowskiEngine-shaped namespace backed by the sm_100a kernels in libpgs_b200.so.
+
+This is the host-side mirror of the part of MinkowskiEngine the reference's hot path touches
+(SURVEY.md section 8b).  Call sites it must satisfy verbatim:
+
+  torch_points3d/applications/minkowski.py:106-111   ME.MinkowskiConvolution / ME.utils.kaiming_normal_
+  torch_points3d/applications/minkowski.py:121-122   ME.SparseTensor(features=, coordinates=, device=)
+  torch_points3d/applications/minkowski.py:150,193   .F / .C
+  torch_points3d/modules/MinkowskiEngine/api_modules.py:9,26-55,244-270,293,308
+                                                     MinkowskiNetwork, MinkowskiConvolution(Transpose),
+                                                     MinkowskiBatchNorm, MinkowskiReLU, cat, `a + b`
+  torch_points3d/core/schedulers/bn_schedulers.py:7-15  MinkowskiBatchNorm / MinkowskiInstanceNorm symbols
+
+Install as a drop-in with  `sys.modules["MinkowskiEngine"] = panopticsegforlargescalepointcloud_b200.me`
+(see INTEGRATION.md).  Semantics frozen in DESIGN.md (row order, kernel-offset enumeration, strided
+and transposed maps).  There is no CPU path: tensors must live on a CUDA device.
+"""
+import math
+import types
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ptr, check, stream_ptr
+
+
+# --------------------------------------------------------------------------------------------
+# coordinate manager
+# --------------------------------------------------------------------------------------------
+class CoordinateMap:
+    """One level of the hierarchy: unique int32 [n,4] coordinates + their device hash table."""
+
+    __slots__ = ("coords", "n", "tkeys", "tvals", "cap", "tensor_stride")
+
+    def __init__(self, coords, n, tkeys, tvals, cap, tensor_stride):
+        self.coords, self.n, self.tkeys, self.tvals, self.cap = coords, n, tkeys, tvals, cap
+        self.tensor_stride = tensor_stride
+
+
+class KernelMap:
+    """Gather table nbr[K, n_q] (+ lazily the ME-style pair lists used by the weight gradient)."""
+
+    __slots__ = ("nbr", "K", "n_q", "_pairs")
+
+    def __init__(self, nbr, K, n_q):
+        self.nbr, self.K, self.n_q = nbr, K, n_q
+        self._pairs = None
+
+    def pairs(self):
+        """(in_idx, out_idx, offs_dev, max_pairs): rulebook grouped by offset, ascending out row."""
+        if self._pairs is None:
+            lib = _lib.load()
+            dev = self.nbr.device
+            total = self.K * self.n_q
+            in_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            out_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+            offs = torch.empty(self.K + 1, dtype=torch.int32, device=dev)
+            nb = lib.pgs_kmap_pairs_scratch_bytes(self.n_q, self.K)
+            scratch = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+            check(lib.pgs_kmap_pairs(ptr(self.nbr), self.n_q, self.K, ptr(in_idx), ptr(out_idx), ptr(offs),
+                                     ptr(scratch), nb, stream_ptr()))
+            offs_h = offs.cpu()
+            npairs = int(offs_h[-1])
+            max_pairs = int((offs_h[1:] - offs_h[:-1]).max()) if self.K > 0 else 0
+            self._pairs = (in_idx[:npairs].clone(), out_idx[:npairs].clone(), offs, max_pairs)
+        return self._pairs
+
+
+class CoordinateManager:
+    """Owns the coordinate maps (one per tensor stride) and kernel maps of one batch."""
+
+    def __init__(self, coordinates: torch.Tensor):
+        if coordinates.dim() != 2 or coordinates.shape[1] != 4:
+            raise ValueError("coordinates must be [N, 1+3] (batch, x, y, z)")
+        if not coordinates.is_cuda:
+            raise _lib.PgsError("coordinates must be on a CUDA device (no CPU path)")
+        self.device = coordinates.device
+        self.maps: Dict[int, CoordinateMap] = {}
+        self.kmaps: Dict[Tuple, KernelMap] = {}
+        self.in2out: Dict[Tuple[int, int], torch.Tensor] = {}
+        coords = coordinates.to(torch.int32).contiguous()
+        m, in2out = self._build(coords, 1)
+        if m.n != coords.shape[0]:
+            raise ValueError(
+                "duplicate coordinates in SparseTensor input (%d rows, %d unique): the reference feeds one "
+                "point per voxel (grid_transform.py:185-194) and indexes outputs positionally" % (coords.shape[0], m.n)
+            )
+        self.maps[1] = m
+
+    def _build(self, coords, ts_out):
+        lib = _lib.load()
+        n = coords.shape[0]
+        dev = coords.device
+        cap = lib.pgs_cmap_capacity(n)
+        tkeys = torch.empty(cap, dtype=torch.int64, device=dev)
+        tvals = torch.empty(cap, dtype=torch.int32, device=dev)
+        out_coords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+        in2out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        meta = torch.zeros(2, dtype=torch.int32, device=dev)  # [n_out, status]
+        nb = lib.pgs_cmap_build_scratch_bytes(n)
+        scratch = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+        check(lib.pgs_cmap_build(ptr(coords), n, ts_out, ptr(tkeys), ptr(tvals), cap, ptr(out_coords),
+                                 ptr(in2out), ptr(meta[0:1]), ptr(meta[1:2]), ptr(scratch), nb, stream_ptr()))
+        n_out, status = meta.tolist()
+        if status & 1:
+            raise ValueError("coordinate outside the supported range (batch < 65536, |xyz| < 32768)")
+        if status & 2:
+            raise _lib.PgsError("coordinate hash table overflow")
+        return CoordinateMap(out_coords[:n_out], n_out, tkeys, tvals, cap, ts_out), in2out[:n]
+
+    def get_map(self, ts: int) -> CoordinateMap:
+        return self.maps[ts]
+
+    def stride(self, ts_in: int, ts_out: int) -> CoordinateMap:
+        if ts_out not in self.maps:
+            m, in2out = self._build(self.maps[ts_in].coords, ts_out)
+            self.maps[ts_out] = m
+            self.in2out[(ts_in, ts_out)] = in2out
+        return self.maps[ts_out]
+
+    def kernel_map(self, ts_q: int, ts_probe: int, step: int, sign: int, ksize: int) -> KernelMap:
+        key = (ts_q, ts_probe, step, sign, ksize)
+        km = self.kmaps.get(key)
+        if km is None:
+            lib = _lib.load()
+            q, p = self.maps[ts_q], self.maps[ts_probe]
+            K = ksize ** 3
+            nbr = torch.empty((K, max(q.n, 1)), dtype=torch.int32, device=self.device)
+            check(lib.pgs_kmap_build(ptr(q.coords), q.n, ptr(p.tkeys), ptr(p.tvals), p.cap, step, sign, ksize,
+                                     ptr(nbr), stream_ptr()))
+            if q.n == 0:
+                nbr = nbr[:, :0]
+            km = KernelMap(nbr, K, q.n)
+            self.kmaps[key] = km
+        return km
+
+
+# --------------------------------------------------------------------------------------------
+# SparseTensor
+# --------------------------------------------------------------------------------------------
+class SparseTensor:
+    """Features F [N,C] fp32 over a coordinate map.  Row i of F belongs to row i of C; for the input
+    tensor that is the caller's row order (the reference relies on it: applications/minkowski.py:193)."""
+
+    def __init__(self, features: torch.Tensor, coordinates: Optional[torch.Tensor] = None, device=None,
+                 tensor_stride: int = 1, coordinate_manager: Optional[CoordinateManager] = None,
+                 coordinate_map_key=None, **_ignored):
+        if device is not None:
+            device = torch.device(device)
+            features = features.to(device)
+            if coordinates is not None:
+                coordinates = coordinates.to(device)
+        if not features.is_cuda:
+            raise _lib.PgsError("SparseTensor features must live on a CUDA device: this backend has no CPU path")
+        if features.dtype != torch.float32:
+            features = features.float()
+        if coordinate_map_key is not None:
+            tensor_stride = int(coordinate_map_key)
+        if coordinate_manager is None:
+            if coordinates is None:
+                raise ValueError("either coordinates or a coordinate_manager is required")
+            coordinate_manager = CoordinateManager(coordinates)
+            tensor_stride = 1
+        self._F = features
+        self.coordinate_manager = coordinate_manager
+        self.tensor_stride = int(tensor_stride)
+        n_map = coordinate_manager.get_map(self.tensor_stride).n
+        if features.shape[0] != n_map:
+            raise ValueError("features have %d rows but the coordinate map has %d" % (features.shape[0], n_map))
+
+    # ME-compatible accessors
+    @property
+    def F(self):
+        return self._F
+
+    features = F
+
+    @property
+    def C(self):
+        return self.coordinate_manager.get_map(self.tensor_stride).coords
+
+    coordinates = C
+
+    @property
+    def coordinate_map_key(self):
+        return self.tensor_stride
+
+    @property
+    def device(self):
+        return self._F.device
+
+    @property
+    def dtype(self):
+        return self._F.dtype
+
+    @property
+    def D(self):
+        return 3
+
+    @property
+    def shape(self):
+        return self._F.shape
+
+    def size(self, *a):
+        return self._F.size(*a)
+
+    def __len__(self):
+        return self._F.shape[0]
+
+    def _like(self, F):
+        return SparseTensor(F, coordinate_manager=self.coordinate_manager, tensor_stride=self.tensor_stride)
+
+    def _check_same_map(self, other):
+        if not isinstance(other, SparseTensor):
+            return
+        if other.coordinate_manager is not self.coordinate_manager or other.tensor_stride != self.tensor_stride:
+            raise ValueError("sparse tensors live on different coordinate maps")
+
+    def __add__(self, other):
+        self._check_same_map(other)
+        return self._like(self._F + (other._F if isinstance(other, SparseTensor) else other))
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        self._check_same_map(other)
+        return self._like(self._F - (other._F if isinstance(other, SparseTensor) else other))
+
+    def __mul__(self, other):
+        self._check_same_map(other)
+        return self._like(self._F * (other._F if isinstance(other, SparseTensor) else other))
+
+    def __repr__(self):
+        return "SparseTensor(n=%d, c=%d, tensor_stride=%d, device=%s)" % (
+            self._F.shape[0], self._F.shape[1], self.tensor_stride, self._F.device)
+
+
+def cat(*tensors):
+    """Channel-wise concatenation of tensors that share a coordinate map (api_modules.py:308)."""
+    if len(tensors) == 1 and isinstance(tensors[0], (list, tuple)):
+        tensors = tuple(tensors[0])
+    first = tensors[0]
+    for t in tensors[1:]:
+        first._check_same_map(t)
+    return first._like(torch.cat([t.F for t in tensors], dim=1))
+
+
+# --------------------------------------------------------------------------------------------
+# convolution
+# --------------------------------------------------------------------------------------------
+def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
+    """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed)."""
+    lib = _lib.load()
+    K = W3.shape[0]
+    c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
+    Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
+    check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
+                           ptr(Y), stream_ptr()))
+    return Y
+
+
+class _SparseConvFn(torch.autograd.Function):
+    """fwd / bwd-input / bwd-weight through the C ABI (pgs_conv_fwd, pgs_conv_bwd_weight)."""
+
+    @staticmethod
+    def forward(ctx, X, W, km_f, km_b, mirror_f, mirror_b, n_out):
+        X = X.contiguous()
+        W3 = W.reshape(-1, W.shape[-2], W.shape[-1]).contiguous()
+        nbr = km_f.nbr if km_f is not None else None
+        Y = _conv_fwd_raw(X, W3, nbr, n_out, mirror_f, False)
+        ctx.save_for_backward(X, W)
+        ctx.km_f, ctx.km_b, ctx.mirror_f, ctx.mirror_b = km_f, km_b, mirror_f, mirror_b
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        dY = dY.contiguous()
+        W3 = W.reshape(-1, W.shape[-2], W.shape[-1]).contiguous()
+        K, c_in, c_out = W3.shape
+        lib = _lib.load()
+        dX = dW = None
+        if ctx.needs_input_grad[0]:
+            nbr_b = ctx.km_b.nbr if ctx.km_b is not None else None
+            dX = _conv_fwd_raw(dY, W3, nbr_b, X.shape[0], ctx.mirror_b, True)
+        if ctx.needs_input_grad[1]:
+            dW3 = torch.zeros_like(W3)
+            if ctx.km_f is not None:
+                in_idx, out_idx, offs, max_pairs = ctx.km_f.pairs()
+                check(lib.pgs_conv_bwd_weight(ptr(X), ptr(dY), ptr(in_idx), ptr(out_idx), ptr(offs), max_pairs,
+                                              K, c_in, c_out, int(ctx.mirror_f), ptr(dW3), stream_ptr()))
+            else:
+                check(lib.pgs_conv_bwd_weight(ptr(X), ptr(dY), None, None, None, X.shape[0], 1, c_in, c_out, 0,
+                                              ptr(dW3), stream_ptr()))
+            dW = dW3.reshape(W.shape)
+        return dX, dW, None, None, None, None, None
+
+
+def _as_int(v, name):
+    if isinstance(v, (list, tuple)):
+        if len(set(v)) != 1:
+            raise NotImplementedError("anisotropic %s is not supported" % name)
+        v = v[0]
+    return int(v)
+
+
+class MinkowskiConvolutionBase(nn.Module):
+    TRANSPOSE = False
+
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=None, dimension=None):
+        super().__init__()
+        if dimension is not None and dimension != 3:
+            raise NotImplementedError("only 3-D sparse convolution is supported")
+        if kernel_generator is not None or expand_coordinates:
+            raise NotImplementedError("custom kernel generators / coordinate expansion are not supported")
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        self.kernel_size = _as_int(kernel_size, "kernel_size")
+        self.stride = _as_int(stride, "stride")
+        self.dilation = _as_int(dilation, "dilation")
+        if self.kernel_size not in (1, 2, 3, 5):
+            raise NotImplementedError("kernel_size %r is not supported" % (kernel_size,))
+        if self.dilation != 1:
+            raise NotImplementedError("dilation != 1 is not used by the reference hot path")
+        if self.kernel_size == 1 and self.stride != 1:
+            raise NotImplementedError("kernel_size 1 with stride > 1")
+        self.kernel_volume = self.kernel_size ** 3
+        self.dimension = 3
+        if self.kernel_volume == 1:
+            self.kernel = nn.Parameter(torch.empty(self.in_channels, self.out_channels))
+        else:
+            self.kernel = nn.Parameter(torch.empty(self.kernel_volume, self.in_channels, self.out_channels))
+        self.bias = nn.Parameter(torch.empty(1, self.out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # ME default: uniform(+-1/sqrt(fan)), fan = Cin*K (conv) or Cout*K (transposed)  [SURVEY App. B.6]
+        with torch.no_grad():
+            n = (self.out_channels if self.TRANSPOSE else self.in_channels) * self.kernel_volume
+            stdv = 1.0 / math.sqrt(n)
+            self.kernel.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.uniform_(-stdv, stdv)
+
+    def _maps(self, x: SparseTensor):
+        """-> (km_fwd, km_bwd, mirror_f, mirror_b, out_tensor_stride, n_out)"""
+        cm, ts = x.coordinate_manager, x.tensor_stride
+        ks = self.kernel_size
+        if not self.TRANSPOSE:
+            if self.stride == 1:
+                if ks == 1:
+                    return None, None, False, False, ts, x.F.shape[0]
+                km = cm.kernel_map(ts, ts, ts, +1, ks)
+                return km, km, False, True, ts, km.n_q
+            ts_out = ts * self.stride
+            coarse = cm.stride(ts, ts_out)
+            km_f = cm.kernel_map(ts_out, ts, ts, +1, ks)
+            km_b = cm.kernel_map(ts, ts_out, ts, -1, ks)
+            return km_f, km_b, False, False, ts_out, coarse.n
+        # transposed
+        if self.stride == 1:
+            if ks == 1:
+                return None, None, False, False, ts, x.F.shape[0]
+            km = cm.kernel_map(ts, ts, ts, +1, ks)
+            return km, km, True, False, ts, km.n_q
+        if ts % self.stride != 0 or (ts // self.stride) not in cm.maps:
+            raise NotImplementedError(
+                "transposed convolution onto a coordinate map that the encoder did not create (tensor stride %d / %d)"
+                % (ts, self.stride))
+        ts_out = ts // self.stride
+        fine = cm.get_map(ts_out)
+        km_f = cm.kernel_map(ts_out, ts, ts_out, -1, ks)
+        km_b = cm.kernel_map(ts, ts_out, ts_out, +1, ks)
+        return km_f, km_b, False, False, ts_out, fine.n
+
+    def forward(self, x: SparseTensor):
+        if x.F.shape[1] != self.in_channels:
+            raise ValueError("expected %d input channels, got %d" % (self.in_channels, x.F.shape[1]))
+        km_f, km_b, mirror_f, mirror_b, ts_out, n_out = self._maps(x)
+        Y = _SparseConvFn.apply(x.F, self.kernel, km_f, km_b, mirror_f, mirror_b, n_out)
+        if self.bias is not None:
+            Y = Y + self.bias
+        return SparseTensor(Y, coordinate_manager=x.coordinate_manager, tensor_stride=ts_out)
+
+    def extra_repr(self):
+        return "in=%d, out=%d, kernel_size=%d, stride=%d, dilation=%d" % (
+            self.in_channels, self.out_channels, self.kernel_size, self.stride, self.dilation)
+
+
+class MinkowskiConvolution(MinkowskiConvolutionBase):
+    TRANSPOSE = False
+
+
+class MinkowskiConvolutionTranspose(MinkowskiConvolutionBase):
+    TRANSPOSE = True
+
+
+# --------------------------------------------------------------------------------------------
+# pointwise modules
+# --------------------------------------------------------------------------------------------
+class MinkowskiNetwork(nn.Module):
+    def __init__(self, D=3):
+        super().__init__()
+        self.D = D
+
+
+class MinkowskiBatchNorm(nn.Module):
+    """nn.BatchNorm1d over all active rows; the inner module is `.bn` (checkpoint key contract)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
+                                 track_running_stats=track_running_stats)
+
+    def forward(self, x: SparseTensor):
+        return x._like(self.bn(x.F))
+
+
+class MinkowskiInstanceNorm(nn.Module):
+    """Symbol required by core/schedulers/bn_schedulers.py:7-15; not used on the hot path."""
+
+    def __init__(self, num_features):
+        super().__init__()
+        self.num_features = num_features
+
+    def forward(self, x):
+        raise NotImplementedError("MinkowskiInstanceNorm is not on the reference hot path")
+
+
+class MinkowskiReLU(nn.Module):
+    def __init__(self, inplace=False):
+        super().__init__()
+
+    def forward(self, x: SparseTensor):
+        return x._like(torch.relu(x.F))
+
+
+class MinkowskiLeakyReLU(nn.Module):
+    def __init__(self, negative_slope=0.01, inplace=False):
+        super().__init__()
+        self.negative_slope = negative_slope
+
+    def forward(self, x: SparseTensor):
+        return x._like(torch.nn.functional.leaky_relu(x.F, self.negative_slope))
+
+
+def _fans(tensor):
+    if tensor.dim() < 2:
+        raise ValueError("fan in / fan out need at least 2 dimensions")
+    if tensor.dim() == 2:  # ME treats a [Cin, Cout] (K == 1) kernel like nn.Linear's [out, in]
+        return tensor.size(1), tensor.size(0)
+    rf = tensor.size(0)
+    return tensor.size(1) * rf, tensor.size(2) * rf
+
+
+def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
+    """ME.utils.kaiming_normal_ for [K, Cin, Cout] kernels (applications/minkowski.py:107)."""
+    fan_in, fan_out = _fans(tensor)
+    fan = fan_in if mode == "fan_in" else fan_out
+    std = nn.init.calculate_gain(nonlinearity, a) / math.sqrt(fan)
+    with torch.no_grad():
+        return tensor.normal_(0, std)
+
+
+utils = types.SimpleNamespace(kaiming_normal_=kaiming_normal_)
+
+__version__ = "0.5.4+b200"
