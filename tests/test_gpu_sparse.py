@@ -1,0 +1,227 @@
+"""GPU parity: coordinate maps, kernel maps (rulebooks) and sparse convolution fwd/bwd through the C ABI
+(libpgs_b200.so) against the numpy oracle (oracle/sparse_ref.py) on the same seeded inputs.
+
+Bars: bit-exact for maps / rulebooks (integer work), 1e-4 for fp32 features and gradients (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sparse_ref as sr
+from oracle import cpu_path
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # fp32 logits/embeddings tolerance stated by BASELINE.json north_star
+
+
+def _me():
+    from panopticsegforlargescalepointcloud_b200 import me
+    return me
+
+
+def _scene(seed, n=20000, batch=2, extent=40, negative=True):
+    rng = np.random.default_rng(seed)
+    rows = []
+    for b in range(batch):
+        c = rng.integers(-extent if negative else 0, extent, (n, 3))
+        c[:, 2] = rng.integers(-3, 4, n)  # surface-like slab
+        c = np.unique(c, axis=0)
+        c = c[rng.permutation(len(c))]
+        rows.append(np.concatenate([np.full((len(c), 1), b), c], 1))
+    return np.concatenate(rows).astype(np.int32)
+
+
+@pytest.mark.parametrize("ts", [1, 2, 4])
+def test_cmap_build_bit_exact(cuda_device, ts):
+    me = _me()
+    coords = _scene(0)
+    mgr = me.CoordinateManager(torch.from_numpy(coords).to(cuda_device))
+    m, in2out = mgr._build(mgr.maps[1].coords, ts)
+    oc, oi = sr.coordinate_map(coords, ts)
+    assert m.n == len(oc)
+    assert np.array_equal(m.coords.cpu().numpy(), oc)
+    assert np.array_equal(in2out.cpu().numpy(), oi)
+
+
+def test_cmap_rejects_duplicates_and_range(cuda_device):
+    me = _me()
+    c = torch.tensor([[0, 1, 1, 1], [0, 1, 1, 1]], dtype=torch.int32, device=cuda_device)
+    with pytest.raises(ValueError):
+        me.CoordinateManager(c)
+    c = torch.tensor([[0, 40000, 1, 1]], dtype=torch.int32, device=cuda_device)
+    with pytest.raises(ValueError):
+        me.CoordinateManager(c)
+
+
+def test_cmap_empty_and_single(cuda_device):
+    me = _me()
+    mgr = me.CoordinateManager(torch.zeros((0, 4), dtype=torch.int32, device=cuda_device))
+    assert mgr.maps[1].n == 0
+    mgr = me.CoordinateManager(torch.tensor([[3, -5, 7, -9]], dtype=torch.int32, device=cuda_device))
+    km = mgr.kernel_map(1, 1, 1, 1, 3)
+    nbr = km.nbr.cpu().numpy()
+    assert nbr[13, 0] == 0 and (np.delete(nbr[:, 0], 13) == -1).all()
+
+
+@pytest.mark.parametrize("case", ["k3s1", "k3s2", "k3s2T", "k2s2", "k3s1_l2"])
+def test_kernel_map_bit_exact(cuda_device, case):
+    me = _me()
+    coords = _scene(1)
+    mgr = me.CoordinateManager(torch.from_numpy(coords).to(cuda_device))
+    maps = sr.Maps(coords)
+    if case == "k3s1":
+        km = mgr.kernel_map(1, 1, 1, +1, 3)
+        ref = maps.kernel_map(1, 1, 1, +1, 3)
+    elif case == "k3s2":
+        mgr.stride(1, 2); maps.stride(1, 2)
+        km = mgr.kernel_map(2, 1, 1, +1, 3)
+        ref = maps.kernel_map(2, 1, 1, +1, 3)
+    elif case == "k3s2T":
+        mgr.stride(1, 2); maps.stride(1, 2)
+        km = mgr.kernel_map(1, 2, 1, -1, 3)
+        ref = maps.kernel_map(1, 2, 1, -1, 3)
+    elif case == "k2s2":
+        mgr.stride(1, 2); maps.stride(1, 2)
+        km = mgr.kernel_map(2, 1, 1, +1, 2)
+        ref = maps.kernel_map(2, 1, 1, +1, 2)
+    else:
+        mgr.stride(1, 2); maps.stride(1, 2)
+        km = mgr.kernel_map(2, 2, 2, +1, 3)
+        ref = maps.kernel_map(2, 2, 2, +1, 3)
+    assert np.array_equal(km.nbr.cpu().numpy(), ref)
+    # ME-style pair lists (rulebook), canonical order
+    i, o, offs, mx = km.pairs()
+    ri, ro, roffs = sr.pairs(ref)
+    assert np.array_equal(offs.cpu().numpy(), roffs)
+    assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(o.cpu().numpy(), ro)
+    assert mx == int(np.diff(roffs).max())
+
+
+@pytest.mark.parametrize("cin,cout", [(4, 16), (16, 16), (32, 48), (96, 112), (192, 80), (5, 7)])
+@pytest.mark.parametrize("mode", ["s1", "s1T", "s2", "s2T"])
+def test_conv_fwd_bwd_parity(cuda_device, cin, cout, mode):
+    me = _me()
+    rng = np.random.default_rng(cin * 1000 + cout)
+    coords = _scene(2, n=6000)
+    ts_in = 2 if mode == "s2T" else 1
+    maps = sr.Maps(coords)
+    mgr = me.CoordinateManager(torch.from_numpy(coords).to(cuda_device))
+    if ts_in == 2:
+        maps.stride(1, 2); mgr.stride(1, 2)
+    n_in = len(maps.coords[ts_in])
+    X = rng.standard_normal((n_in, cin)).astype(np.float32)
+    W = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    stride = 2 if mode in ("s2", "s2T") else 1
+    transpose = mode.endswith("T")
+    nbr_f, mir_f, nbr_b, mir_b, ts_out = maps.conv_maps(ts_in, 3, stride, transpose)
+    Yr = sr.conv_fwd(X, W, nbr_f, mirror=mir_f)
+    dY = rng.standard_normal(Yr.shape).astype(np.float32)
+    dXr, dWr = sr.conv_bwd(X, W, dY, nbr_f, mirror=mir_f)
+
+    cls = me.MinkowskiConvolutionTranspose if transpose else me.MinkowskiConvolution
+    conv = cls(cin, cout, kernel_size=3, stride=stride, dimension=3).to(cuda_device)
+    with torch.no_grad():
+        conv.kernel.copy_(torch.from_numpy(W))
+    Xt = torch.from_numpy(X).to(cuda_device).requires_grad_(True)
+    xin = me.SparseTensor(Xt, coordinate_manager=mgr, tensor_stride=ts_in)
+    out = conv(xin)
+    assert out.tensor_stride == ts_out
+    out.F.backward(torch.from_numpy(dY).to(cuda_device))
+    assert np.allclose(out.F.detach().cpu().numpy(), Yr, atol=TOL, rtol=TOL)
+    assert np.allclose(Xt.grad.cpu().numpy(), dXr, atol=TOL, rtol=TOL)
+    assert np.allclose(conv.kernel.grad.cpu().numpy(), dWr, atol=TOL * 10, rtol=TOL)  # sums over ~1e4 pairs
+
+
+def test_conv_k1_parity(cuda_device):
+    me = _me()
+    rng = np.random.default_rng(5)
+    coords = _scene(3, n=3000)
+    X = rng.standard_normal((len(coords), 48)).astype(np.float32)
+    W = (rng.standard_normal((48, 64)) / 7).astype(np.float32)
+    conv = me.MinkowskiConvolution(48, 64, kernel_size=1, stride=1, dimension=3).to(cuda_device)
+    with torch.no_grad():
+        conv.kernel.copy_(torch.from_numpy(W))
+    Xt = torch.from_numpy(X).to(cuda_device).requires_grad_(True)
+    out = conv(me.SparseTensor(Xt, coordinates=torch.from_numpy(coords).to(cuda_device)))
+    dY = rng.standard_normal((len(coords), 64)).astype(np.float32)
+    out.F.backward(torch.from_numpy(dY).to(cuda_device))
+    dXr, dWr = sr.conv_bwd(X, W, dY, None)
+    assert np.allclose(out.F.detach().cpu().numpy(), X @ W, atol=TOL, rtol=TOL)
+    assert np.allclose(Xt.grad.cpu().numpy(), dXr, atol=TOL, rtol=TOL)
+    assert np.allclose(conv.kernel.grad.cpu().numpy(), dWr, atol=TOL * 10, rtol=TOL)
+
+
+def _batch(coords_b, x, dev):
+    class D:
+        pass
+    d = D()
+    d.batch = torch.from_numpy(coords_b[:, 0].astype(np.int64)).to(dev)
+    d.coords = torch.from_numpy(coords_b[:, 1:].copy()).to(dev)
+    d.x = torch.from_numpy(x).to(dev)
+    d.pos = d.coords.float()
+    return d
+
+
+@pytest.mark.parametrize("which,training", [("two_level", True), ("two_level", False), ("paper", True)])
+def test_unet_forward_backward_parity(cuda_device, which, training):
+    """Full backbone through the product modules vs the functional CPU restatement, same state_dict."""
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb
+    torch.manual_seed(2022)
+    cfg = bb.two_level_config(16) if which == "two_level" else bb.paper_backbone_config(16)
+    net = bb.Minkowski("unet", input_nc=4, config=cfg).to(cuda_device)
+    net.train(training)
+    rng = np.random.default_rng(11)
+    coords = _scene(4, n=15000 if which == "paper" else 8000, extent=64)
+    x = rng.standard_normal((len(coords), 4)).astype(np.float32)
+    with torch.no_grad():  # non-trivial running stats for the eval-mode case
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.uniform_(-0.1, 0.1)
+                m.running_var.uniform_(0.8, 1.2)
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    out = net(_batch(coords, x, cuda_device)).x
+    g = torch.from_numpy(rng.standard_normal(tuple(out.shape)).astype(np.float32))
+    out.backward(g.to(cuda_device))
+
+    sd_ref = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    ref = cpu_path.unet_forward(sd_ref, cpu_path.resolve_cfg(cfg, 4), torch.from_numpy(x), coords, training=training)
+    ref.backward(g)
+    scale = max(float(ref.abs().max()), 1.0)
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= TOL * scale
+    worst = 0.0
+    for name, p in net.named_parameters():
+        gr = sd_ref[name].grad
+        assert gr is not None, name
+        denom = max(float(gr.abs().max()), 1.0)
+        worst = max(worst, float((p.grad.cpu() - gr).abs().max()) / denom)
+    # gradients run through up to 82 conv+BN layers; 1e-3 relative to the largest entry per tensor
+    assert worst <= 1e-3, worst
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE size (200k voxels): size-independent properties instead of the slow oracle:
+    identity map at stride 1, centre offset == self, pair symmetry (k <-> 26-k), strided-map swap symmetry."""
+    me = _me()
+    from panopticsegforlargescalepointcloud_b200 import scenes
+    s = scenes.make_scene("urban", 200000, 0.12, 16.0, seed=0)
+    c = np.concatenate([np.zeros((len(s.coords), 1), np.int32), s.coords], 1)
+    mgr = me.CoordinateManager(torch.from_numpy(c).to(cuda_device))
+    km = mgr.kernel_map(1, 1, 1, 1, 3)
+    n = len(c)
+    ar = torch.arange(n, device=cuda_device, dtype=torch.int32)
+    assert torch.equal(km.nbr[13], ar)
+    for k in range(13):
+        a, b = km.nbr[k], km.nbr[26 - k]
+        q = torch.nonzero(a >= 0).squeeze(1)
+        assert torch.equal(b[a[q].long()], q.int())          # q --k--> r  implies  r --(26-k)--> q
+        assert int((a >= 0).sum()) == int((b >= 0).sum())
+    coarse = mgr.stride(1, 2)
+    dn = mgr.kernel_map(2, 1, 1, +1, 3).nbr
+    up = mgr.kernel_map(1, 2, 1, -1, 3).nbr
+    assert int((dn >= 0).sum()) == int((up >= 0).sum())
+    for k in (0, 13, 26):
+        o = torch.nonzero(dn[k] >= 0).squeeze(1)
+        assert torch.equal(up[k][dn[k][o].long()], o.int())
+    # every fine row maps into exactly one coarse row through exactly one of the 8 "child" offsets
+    child = torch.stack([up[k] for k in (13, 14, 16, 17, 22, 23, 25, 26)])
+    assert coarse.n < n and int((child >= 0).sum(0).min()) == 1 and int((child >= 0).sum(0).max()) == 1
