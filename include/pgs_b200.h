@@ -118,6 +118,55 @@ int pgs_conv_bwd_weight(const float* X, const float* dY,
                         int64_t max_pairs, int32_t K, int32_t c_in, int32_t c_out, int32_t mirror,
                         float* dW, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Ball query + region growing  (replaces torch_points_kernels.ball_query(mode="PARTIAL_DENSE") and
+ *                               torch_points_kernels.region_grow -- un-vendored dependency, tpk 0.7.0;
+ *                               reference: torch_points3d/models/panoptic/PointGroup3heads.py:166-174,
+ *                               185-202,296-304,340-357; core/spatial_ops/neighbour_finder.py:35-37,164)
+ *
+ * gid[i] >= 0 is the group (scene, or semantic class x scene) of support/query point i; points only see
+ * points of their own group; gid < 0 = not a support point / no neighbours.  gid < 32767.
+ * Neighbour list of a query = the FIRST nsample support points of its group, in ascending row index,
+ * with fp32 d2 = fma(dz,dz,fma(dy,dy,dx*dx)) <= radius*radius  (the upstream kernel's scan order).
+ *
+ * Grid: cells of edge `cell` >= radius; rows sorted by (gid, cell) then row index.
+ *   spos        float4 [n]     (x, y, z, bit-cast row index) in sorted order
+ *   skeys       uint64 [n]     sorted cell keys (all-ones = not a support point)
+ *   tkeys/tvals hash cell key -> cell ordinal, capacity `cap` (pgs_cmap_capacity(n))
+ *   cell_start  int32 [n+1]    rows of cell c are [cell_start[c], cell_start[c+1])
+ *   meta        int32 [2]      {#support rows, #cells}
+ *   status      uint32 [1]     PGS_STATUS_COORD_RANGE if a point does not fit +-32766 cells (caller zeroes)
+ * ------------------------------------------------------------------------------------------ */
+size_t pgs_bq_grid_scratch_bytes(int64_t n);
+int pgs_bq_grid_build(const float* pos, const int32_t* gid, int64_t n, float cell,
+                      uint64_t* tkeys, int32_t* tvals, int64_t cap,
+                      float* spos, uint64_t* skeys, int32_t* cell_start, int32_t* meta,
+                      uint32_t* status, void* scratch, size_t scratch_bytes, void* stream);
+
+/* queries that are not the support set: qpos float4 [n] (x,y,z,row), qkeys uint64 [n], input order */
+int pgs_bq_pack_queries(const float* pos, const int32_t* gid, int64_t n, float cell,
+                        float* qpos, uint64_t* qkeys, void* stream);
+
+/* One warp per query.  For self-queries pass qpos = spos, qkeys = skeys.
+ *   nbr  int32 [n_rows, nsample]  row = query's row index; first cnt[row] entries valid (unordered unless
+ *                                 the row is full, in which case it holds the nsample smallest indices)
+ *   cnt  int32 [n_rows]           zeroed here for the first n_q rows
+ *   dist fp32  [n_rows, nsample]  squared distances, same layout (may be NULL) */
+int pgs_bq_query(const float* spos, const float* qpos, const uint64_t* qkeys, int64_t n_q,
+                 const uint64_t* tkeys, const int32_t* tvals, int64_t cap, const int32_t* cell_start,
+                 float radius, int32_t nsample, int32_t* nbr, int32_t* cnt, float* dist, void* stream);
+
+/* reference layout: idx int64 [n, nsample] ascending, -1 padded; dist2 fp32 [n, nsample], -1 padded */
+int pgs_bq_export(const int32_t* nbr, const float* dist, const int32_t* cnt, int64_t n, int32_t nsample,
+                  int64_t* idx_out, float* dist_out, void* stream);
+
+/* Region growing == min-ancestor labelling over the directed edges q -> nbr[q][*]:
+ * label[v] = smallest row index that reaches v.  pgs_rg_propagate runs `rounds` (push + pointer-jump)
+ * sweeps and leaves *changed != 0 if any label moved; call until it reads 0. */
+int pgs_rg_init(const int32_t* gid, int64_t n, int32_t* label, void* stream);
+int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid, int64_t n, int32_t nsample,
+                     int32_t rounds, int32_t* label, int32_t* changed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,16 @@ SIGNATURES = {
                                c_void_p]),
     "pgs_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                              c_int32, c_void_p, c_void_p]),
+    "pgs_bq_grid_scratch_bytes": (c_size_t, [c_int64]),
+    "pgs_bq_grid_build": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pgs_bq_pack_queries": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "pgs_bq_query": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_float,
+                             c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgs_bq_export": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgs_rg_init": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "pgs_rg_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                 c_void_p]),
     "pgs_conv_bwd_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     c_int32, c_int32, c_int32, c_void_p, c_void_p]),
 }
