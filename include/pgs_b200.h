@@ -167,6 +167,30 @@ int pgs_rg_init(const int32_t* gid, int64_t n, int32_t* label, void* stream);
 int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid, int64_t n, int32_t nsample,
                      int32_t rounds, int32_t* label, int32_t* changed, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HDBSCAN  (replaces hdbscan.HDBSCAN(min_cluster_size, min_samples, cluster_selection_epsilon).fit_predict --
+ *           un-vendored dependency hdbscan 0.8.27; reference: torch_points3d/utils/hdbscan_cluster.py:8-13,
+ *           117-167; models/panoptic/pointgroupembed.py:240-245,704; models/panoptic/pointgroup.py:208-212)
+ *
+ * pgs_hdb_mst (device): float64 core distances (distance to the min_samples-th nearest sample counting the
+ * sample itself) and the exact minimum spanning tree of the mutual-reachability graph
+ * w(a,b) = max(core_a, core_b, d(a,b)/alpha) under the strict order (w, min(a,b), max(a,b)).
+ *   X     fp32 [n, D] row-major, 1 <= D <= 8            core  fp64 [n]
+ *   u, v  int32 [n-1] (u < v, original row ids)         w     fp64 [n-1]   sorted by the strict order
+ * Synchronises `stream` once per Boruvka round (the round count is data dependent); *rounds_host receives it.
+ *
+ * pgs_hdb_labels_host (host, sequential O(n)): sorted MST -> single linkage -> condensed tree -> excess of
+ * mass + epsilon selection -> labels (-1 = noise; clusters numbered by ascending condensed-tree id).
+ * All pointers of this function are HOST pointers.
+ * ------------------------------------------------------------------------------------------ */
+size_t pgs_hdb_scratch_bytes(int64_t n, int32_t D);
+int pgs_hdb_mst(const float* X, int64_t n, int32_t D, int32_t min_samples, double alpha,
+                double* core, int32_t* u, int32_t* v, double* w, int32_t* rounds_host,
+                void* scratch, size_t scratch_bytes, void* stream);
+int pgs_hdb_labels_host(const int32_t* u_host, const int32_t* v_host, const double* w_host, int64_t n,
+                        int32_t min_cluster_size, double cluster_selection_epsilon,
+                        int32_t* labels_host, int32_t* n_clusters_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,587 @@
+// HDBSCAN front half on the device: k-NN core distances and the exact mutual-reachability minimum
+// spanning tree (Boruvka), float64 arithmetic.
+//
+// Replaces hdbscan 0.8.27's KD-tree / dual-tree Boruvka (Cython, CPU) that the reference reaches through
+// torch_points3d/utils/hdbscan_cluster.py:8-13,117-167 (and pointgroupembed.py:240-245,704;
+// pointgroup.py:208-212).  Published algorithm: SURVEY App. D steps 1-3; scikit-learn's statement of the
+// same steps: sklearn/cluster/_hdbscan/hdbscan.py:343-360, _linkage.pyx:111-223.
+//
+// Layout: points are sorted by a D-dimensional Morton code and cut into leaf blocks of 32 consecutive
+// points with an axis-aligned box each.  One warp owns one query block (lane = query point) and sweeps ALL
+// candidate blocks outward from its own position: 32 boxes are tested per step (one per lane, box-to-box
+// lower bound against the warp's current pruning bound, plus "same component" and "minimum core distance"
+// rejections in the Boruvka rounds), surviving blocks are staged through shared memory and evaluated
+// 32 x 32.  No tree, no stack: the sweep is a coalesced stream over nb * 2D floats that lives in L2.
+//
+// Determinism: edge weights are float64 with one rounding per operation in the order
+// d = sqrt(((t0^2 + t1^2) + t2^2) + ...), w = max(core_a, core_b, d / alpha); edges are strictly ordered by
+// (w, min(a,b), max(a,b)) with ORIGINAL row ids, so the MST is unique and bit-identical to the oracle's Prim.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace pgs {
+
+constexpr int kHB = 32;        // points per leaf block
+constexpr int kHT = 256;       // threads per CTA (8 warps)
+constexpr uint64_t kU64Max = ~0ull;
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// mm[0..D) = ordered-uint min, mm[D..2D) = ordered-uint max  (caller: min init 0xffffffff, max init 0)
+__global__ void __launch_bounds__(kHT) hdb_bbox_kernel(const float* __restrict__ X, int64_t n, int D,
+                                                        unsigned* __restrict__ mm, uint32_t* __restrict__ status) {
+  for (int d = 0; d < D; ++d) {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float x = X[i * D + d];
+      if (!(fabsf(x) <= FLT_MAX)) atomicOr(status, PGS_STATUS_COORD_RANGE);  // NaN / inf
+      const unsigned o = f2ord(x);
+      lo = min(lo, o);
+      hi = max(hi, o);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&mm[d], lo);
+      atomicMax(&mm[D + d], hi);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kHT) hdb_morton_kernel(const float* __restrict__ X, int64_t n, int D,
+                                                          const unsigned* __restrict__ mm,
+                                                          uint64_t* __restrict__ keys, int32_t* __restrict__ ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int bits = min(60 / D, 21);
+  uint64_t key = 0;
+  for (int d = 0; d < D; ++d) {
+    const float lo = ord2f(mm[d]), hi = ord2f(mm[D + d]);
+    const float span = hi - lo;
+    float t = span > 0.f ? (X[i * D + d] - lo) / span : 0.f;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    const uint32_t q = (uint32_t)(t * (float)((1u << bits) - 1u));
+    for (int b = 0; b < bits; ++b) key |= (uint64_t)((q >> b) & 1u) << (b * D + d);
+  }
+  keys[i] = key;
+  ids[i] = (int32_t)i;
+}
+
+// sorted rows P [n, D] fp32, original ids, inverse permutation
+__global__ void __launch_bounds__(kHT) hdb_gather_kernel(const float* __restrict__ X, const int32_t* __restrict__ sids,
+                                                          int64_t n, int D, float* __restrict__ P,
+                                                          int32_t* __restrict__ inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int id = sids[i];
+  inv[id] = (int32_t)i;
+  for (int d = 0; d < D; ++d) P[i * D + d] = X[(int64_t)id * D + d];
+}
+
+// one warp per leaf block: box lo/hi per dimension
+template <int D>
+__global__ void __launch_bounds__(kHT) hdb_block_box_kernel(const float* __restrict__ P, int64_t n, int nb,
+                                                             float* __restrict__ blo, float* __restrict__ bhi) {
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (b >= nb) return;
+  const int64_t i = (int64_t)b * kHB + lane;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    if (i < n) lo = hi = P[i * D + d];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if (lane == 0) {
+      blo[(int64_t)b * D + d] = lo;
+      bhi[(int64_t)b * D + d] = hi;
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+
+// squared distance, one rounding per operation (no FMA contraction), dimension order 0..D-1
+template <int D>
+__device__ __forceinline__ double sqdist_rn(const double* q, const float* p) {
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double t = __dsub_rn(q[d], (double)p[d]);
+    s = __dadd_rn(s, __dmul_rn(t, t));
+  }
+  return s;
+}
+
+// lower bound of the squared distance between two boxes; every term is <= the matching term of any
+// point pair inside the boxes and rounding is monotone, so lb <= sqdist_rn of every such pair.
+template <int D>
+__device__ __forceinline__ double box_box_lb2(const float* qlo, const float* qhi, const float* __restrict__ clo,
+                                              const float* __restrict__ chi) {
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double g1 = __dsub_rn((double)clo[d], (double)qhi[d]);
+    const double g2 = __dsub_rn((double)qlo[d], (double)chi[d]);
+    const double g = fmax(fmax(g1, g2), 0.0);
+    s = __dadd_rn(s, __dmul_rn(g, g));
+  }
+  return s;
+}
+
+// candidate block visited at step t of the outward sweep from block qb
+__device__ __forceinline__ int sweep_block(int qb, int t) { return (t & 1) ? qb + ((t + 1) >> 1) : qb - (t >> 1); }
+
+// ------------------------------------------------------------------------------------------
+// core distances: k-th smallest distance counting the point itself
+// ------------------------------------------------------------------------------------------
+template <int D, int KMAX>
+__global__ void __launch_bounds__(kHT) hdb_knn_kernel(const float* __restrict__ P, const int32_t* __restrict__ sids,
+                                                       int64_t n, int nb, const float* __restrict__ blo,
+                                                       const float* __restrict__ bhi, int k,
+                                                       double* __restrict__ core_sorted,
+                                                       double* __restrict__ core_orig) {
+  __shared__ float s_pts[kHT / 32][kHB * D];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int qb = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (qb >= nb) return;
+  const int64_t a = (int64_t)qb * kHB + lane;
+  const bool valid = a < n;
+  double q[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) q[d] = valid ? (double)P[a * D + d] : 0.0;
+  float qlo[D], qhi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    qlo[d] = blo[(int64_t)qb * D + d];
+    qhi[d] = bhi[(int64_t)qb * D + d];
+  }
+  double best[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) best[j] = (valid && j < k) ? INFINITY : -1.0;
+  // best[0..k) ascending; entries >= k are -1 and never move
+  double kth = valid ? INFINITY : -1.0;
+  double wb = INFINITY;
+
+  const int span = 2 * max(qb, nb - 1 - qb) + 1;
+  for (int base = 0; base < span; base += 32) {
+    const int cb = sweep_block(qb, base + lane);
+    bool pass = cb >= 0 && cb < nb;
+    if (pass) pass = box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb;
+    unsigned mask = __ballot_sync(0xffffffffu, pass);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int blk = __shfl_sync(0xffffffffu, cb, src);
+      const int64_t p0 = (int64_t)blk * kHB;
+      const int cnt = (int)min((int64_t)kHB, n - p0);
+      __syncwarp();
+      for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
+      __syncwarp();
+      if (valid) {
+        for (int j = 0; j < cnt; ++j) {
+          double x = sqdist_rn<D>(q, &s_pts[wib][j * D]);
+          if (x < kth) {
+#pragma unroll
+            for (int m = 0; m < KMAX; ++m)
+              if (m < k && x < best[m]) {
+                const double t = best[m];
+                best[m] = x;
+                x = t;
+              }
+#pragma unroll
+            for (int m = 0; m < KMAX; ++m)
+              if (m == k - 1) kth = best[m];
+          }
+        }
+      }
+      wb = warp_max_d(kth);
+    }
+  }
+  if (valid) {
+    const double c = __dsqrt_rn(kth);
+    core_sorted[a] = c;
+    core_orig[sids[a]] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Boruvka rounds
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kHT) hdb_block_core_kernel(const double* __restrict__ core_sorted, int64_t n, int nb,
+                                                              double* __restrict__ bmincore) {
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (b >= nb) return;
+  const int64_t i = (int64_t)b * kHB + lane;
+  double c = i < n ? core_sorted[i] : INFINITY;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) c = fmin(c, __shfl_xor_sync(0xffffffffu, c, s));
+  if (lane == 0) bmincore[b] = c;
+}
+
+__global__ void __launch_bounds__(kHT) hdb_round_init_kernel(const int32_t* __restrict__ comp, int64_t n, int nb,
+                                                              int32_t* __restrict__ bcomp, uint64_t* __restrict__ U,
+                                                              uint64_t* __restrict__ E) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    U[i] = kU64Max;
+    E[i] = kU64Max;
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t b = i >> 5;
+  if (b < nb) {
+    const int c = i < n ? comp[i] : -2;
+    const int c0 = __shfl_sync(0xffffffffu, c, 0);
+    const bool same = (c == c0) || (c == -2);
+    const bool uni = __all_sync(0xffffffffu, same);
+    if (lane == 0) bcomp[b] = uni ? c0 : -1;
+  }
+}
+
+__device__ __forceinline__ double u2d(uint64_t u) { return u == kU64Max ? INFINITY : __longlong_as_double((long long)u); }
+
+template <int D>
+__global__ void __launch_bounds__(kHT) hdb_search_kernel(
+    const float* __restrict__ P, const int32_t* __restrict__ sids, const double* __restrict__ core_sorted,
+    const int32_t* __restrict__ comp, int64_t n, int nb, const float* __restrict__ blo, const float* __restrict__ bhi,
+    const double* __restrict__ bmincore, const int32_t* __restrict__ bcomp, double alpha,
+    uint64_t* __restrict__ U, double* __restrict__ bestw, int32_t* __restrict__ bestp) {
+  __shared__ float s_pts[kHT / 32][kHB * D];
+  __shared__ double s_core[kHT / 32][kHB];
+  __shared__ int s_comp[kHT / 32][kHB];
+  __shared__ int s_oid[kHT / 32][kHB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int qb = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (qb >= nb) return;
+  const int64_t a = (int64_t)qb * kHB + lane;
+  const bool valid = a < n;
+  double q[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) q[d] = valid ? (double)P[a * D + d] : 0.0;
+  float qlo[D], qhi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    qlo[d] = blo[(int64_t)qb * D + d];
+    qhi[d] = bhi[(int64_t)qb * D + d];
+  }
+  const int ca = valid ? comp[a] : -3;
+  const double core_a = valid ? core_sorted[a] : INFINITY;
+  const int oa = valid ? sids[a] : 0;
+  const int qc = bcomp[qb];
+  const double qmin = bmincore[qb];
+
+  double bw = INFINITY;  // best weight
+  int bj = -1, blo_id = 0x7fffffff, bhi_id = 0x7fffffff;
+  double published = INFINITY;
+
+  const int span = 2 * max(qb, nb - 1 - qb) + 1;
+  for (int base = 0; base < span; base += 32) {
+    // pruning bound: my best so far and whatever my component has already published
+    double bnd = valid ? fmin(bw, u2d(*(volatile uint64_t*)&U[ca])) : -1.0;
+    if (core_a > bnd) bnd = -1.0;  // nothing at this lane can still win (w >= core_a)
+    const double wb = warp_max_d(bnd);
+    if (wb < 0.0) break;           // every lane of the block is settled
+    const double wba = wb * alpha;                              // bound on the raw distance (w >= d / alpha)
+    const double wb2 = wba * wba * (1.0 + 8.0 * DBL_EPSILON);  // squared-space bound, rounded up
+    const int cb = sweep_block(qb, base + lane);
+    bool pass = cb >= 0 && cb < nb;
+    if (pass) {
+      const int bc = bcomp[cb];
+      pass = !(qc >= 0 && bc == qc) && fmax(bmincore[cb], qmin) <= wb &&
+             box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb2;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, pass);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int blk = __shfl_sync(0xffffffffu, cb, src);
+      const int64_t p0 = (int64_t)blk * kHB;
+      const int cnt = (int)min((int64_t)kHB, n - p0);
+      __syncwarp();
+      for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
+      if (lane < cnt) {
+        s_core[wib][lane] = core_sorted[p0 + lane];
+        s_comp[wib][lane] = comp[p0 + lane];
+        s_oid[wib][lane] = sids[p0 + lane];
+      }
+      __syncwarp();
+      if (bnd >= 0.0) {
+        for (int j = 0; j < cnt; ++j) {
+          if (s_comp[wib][j] == ca) continue;
+          double w = fmax(core_a, s_core[wib][j]);
+          if (w > bnd) continue;
+          const double d2 = sqdist_rn<D>(q, &s_pts[wib][j * D]);
+          const double ba = bnd * alpha;
+          if (d2 > ba * ba * (1.0 + 8.0 * DBL_EPSILON)) continue;
+          const double dist = __ddiv_rn(__dsqrt_rn(d2), alpha);
+          w = fmax(w, dist);
+          const int oj = s_oid[wib][j];
+          const int lo = min(oa, oj), hi = max(oa, oj);
+          const bool better = (w < bw) || (w == bw && (lo < blo_id || (lo == blo_id && hi < bhi_id)));
+          if (better) {
+            bw = w;
+            bj = (int)(p0 + j);
+            blo_id = lo;
+            bhi_id = hi;
+            if (w < bnd) bnd = w;
+          }
+        }
+      }
+    }
+    if (valid && bw < published) {
+      atomicMin((unsigned long long*)&U[ca], (unsigned long long)__double_as_longlong(bw));
+      published = bw;
+    }
+  }
+  if (valid) {
+    bestw[a] = bw;
+    bestp[a] = bj;
+    if (bw < published) atomicMin((unsigned long long*)&U[ca], (unsigned long long)__double_as_longlong(bw));
+  }
+}
+
+// among the points that hold their component's minimum weight, the smallest (min id, max id) wins
+__global__ void __launch_bounds__(kHT) hdb_select_kernel(const int32_t* __restrict__ sids,
+                                                          const int32_t* __restrict__ comp,
+                                                          const double* __restrict__ bestw,
+                                                          const int32_t* __restrict__ bestp, int64_t n,
+                                                          const uint64_t* __restrict__ U, uint64_t* __restrict__ E) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int j = bestp[a];
+  if (j < 0) return;
+  const int c = comp[a];
+  if ((uint64_t)__double_as_longlong(bestw[a]) != U[c]) return;
+  const unsigned oa = (unsigned)sids[a], oj = (unsigned)sids[j];
+  const uint64_t e = ((uint64_t)min(oa, oj) << 32) | (uint64_t)max(oa, oj);
+  atomicMin((unsigned long long*)&E[c], (unsigned long long)e);
+}
+
+// one thread per component representative: emit its edge (once per mutual pair) and hook
+__global__ void __launch_bounds__(kHT) hdb_merge_kernel(const int32_t* __restrict__ comp, const int32_t* __restrict__ inv,
+                                                         int64_t n, const uint64_t* __restrict__ U,
+                                                         const uint64_t* __restrict__ E, int32_t* __restrict__ next,
+                                                         uint64_t* __restrict__ edge_uv, double* __restrict__ edge_w,
+                                                         int32_t* __restrict__ n_edges) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  if (comp[c] != (int32_t)c) return;
+  next[c] = (int32_t)c;
+  const uint64_t e = E[c];
+  if (e == kU64Max) return;
+  const int pa = inv[(int32_t)(e >> 32)], pb = inv[(int32_t)(e & 0xffffffffu)];
+  const int ca = comp[pa], cb = comp[pb];
+  const int other = (ca == (int32_t)c) ? cb : ca;
+  const bool mutual = E[other] == e;
+  if (!mutual || (int32_t)c < other) {
+    const int slot = atomicAdd(n_edges, 1);
+    edge_uv[slot] = e;
+    edge_w[slot] = u2d(U[c]);
+  }
+  if (!(mutual && (int32_t)c < other)) next[c] = other;
+}
+
+__global__ void __launch_bounds__(kHT) hdb_relabel_kernel(int32_t* __restrict__ comp, const int32_t* __restrict__ next,
+                                                           int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = comp[i];
+  for (;;) {
+    const int p = next[c];
+    if (p == c) break;
+    c = p;
+  }
+  comp[i] = c;
+}
+
+__global__ void __launch_bounds__(kHT) hdb_iota_kernel(int32_t* __restrict__ v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(kHT) hdb_unpack_kernel(const uint64_t* __restrict__ uv, int64_t m,
+                                                          int32_t* __restrict__ u, int32_t* __restrict__ v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  u[i] = (int32_t)(uv[i] >> 32);
+  v[i] = (int32_t)(uv[i] & 0xffffffffu);
+}
+
+struct HdbLayout {
+  unsigned* mm;
+  uint32_t* status;
+  int32_t* n_edges;
+  uint64_t *keys, *skeys, *U, *E, *edge_uv, *edge_uv2;
+  int32_t *ids, *sids, *inv, *comp, *next, *bcomp, *bestp;
+  float *P, *blo, *bhi;
+  double *core_sorted, *bmincore, *bestw, *edge_w, *edge_w2;
+  void* cub_ws;
+  size_t cub_bytes, total;
+};
+
+static HdbLayout hdb_layout(int64_t n, int D, void* base) {
+  HdbLayout L;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) {
+    char* r = p;
+    p += align_up(bytes ? bytes : 1, 256);
+    return r;
+  };
+  const int64_t nb = (n + kHB - 1) / kHB;
+  L.mm = (unsigned*)take(sizeof(unsigned) * 2 * D);
+  L.status = (uint32_t*)take(sizeof(uint32_t));
+  L.n_edges = (int32_t*)take(sizeof(int32_t));
+  L.keys = (uint64_t*)take(8 * n);
+  L.skeys = (uint64_t*)take(8 * n);
+  L.U = (uint64_t*)take(8 * n);
+  L.E = (uint64_t*)take(8 * n);
+  L.edge_uv = (uint64_t*)take(8 * n);
+  L.edge_uv2 = (uint64_t*)take(8 * n);
+  L.ids = (int32_t*)take(4 * n);
+  L.sids = (int32_t*)take(4 * n);
+  L.inv = (int32_t*)take(4 * n);
+  L.comp = (int32_t*)take(4 * n);
+  L.next = (int32_t*)take(4 * n);
+  L.bcomp = (int32_t*)take(4 * nb);
+  L.bestp = (int32_t*)take(4 * n);
+  L.P = (float*)take(4 * n * D);
+  L.blo = (float*)take(4 * nb * D);
+  L.bhi = (float*)take(4 * nb * D);
+  L.core_sorted = (double*)take(8 * n);
+  L.bmincore = (double*)take(8 * nb);
+  L.bestw = (double*)take(8 * n);
+  L.edge_w = (double*)take(8 * n);
+  L.edge_w2 = (double*)take(8 * n);
+  size_t b1 = 0, b2 = 0, b3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)n);
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const double*)nullptr,
+                                  (double*)nullptr, (int)n);
+  cub::DeviceRadixSort::SortPairs(nullptr, b3, (const double*)nullptr, (double*)nullptr, (const uint64_t*)nullptr,
+                                  (uint64_t*)nullptr, (int)n);
+  L.cub_bytes = b1 > b2 ? (b1 > b3 ? b1 : b3) : (b2 > b3 ? b2 : b3);
+  L.cub_ws = take(L.cub_bytes);
+  L.total = (size_t)(p - (char*)base);
+  return L;
+}
+
+static inline unsigned blocks_for(int64_t threads) { return (unsigned)((threads + kHT - 1) / kHT); }
+
+template <int D>
+static int hdb_mst_impl(const float* X, int64_t n, int k, double alpha, double* core, int32_t* u, int32_t* v, double* w,
+                        int32_t* rounds_host, HdbLayout& L, cudaStream_t s) {
+  const int nb = (int)((n + kHB - 1) / kHB);
+  const unsigned gp = blocks_for(n), gw = blocks_for((int64_t)nb * 32);
+  PGS_CUDA(cudaMemsetAsync(L.mm, 0xff, sizeof(unsigned) * D, s));
+  PGS_CUDA(cudaMemsetAsync(L.mm + D, 0x00, sizeof(unsigned) * D, s));
+  PGS_CUDA(cudaMemsetAsync(L.status, 0, sizeof(uint32_t), s));
+  PGS_CUDA(cudaMemsetAsync(L.n_edges, 0, sizeof(int32_t), s));
+  hdb_bbox_kernel<<<min(gp, (unsigned)(kNumSM * 8)), kHT, 0, s>>>(X, n, D, L.mm, L.status);
+  hdb_morton_kernel<<<gp, kHT, 0, s>>>(X, n, D, L.mm, L.keys, L.ids);
+  count_launch(2);
+  size_t cb = L.cub_bytes;
+  PGS_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_ws, cb, L.keys, L.skeys, L.ids, L.sids, (int)n, 0, 64, s));
+  hdb_gather_kernel<<<gp, kHT, 0, s>>>(X, L.sids, n, D, L.P, L.inv);
+  hdb_block_box_kernel<D><<<gw, kHT, 0, s>>>(L.P, n, nb, L.blo, L.bhi);
+  count_launch(2);
+  if (k <= 8)
+    hdb_knn_kernel<D, 8><<<gw, kHT, 0, s>>>(L.P, L.sids, n, nb, L.blo, L.bhi, k, L.core_sorted, core);
+  else
+    hdb_knn_kernel<D, 32><<<gw, kHT, 0, s>>>(L.P, L.sids, n, nb, L.blo, L.bhi, k, L.core_sorted, core);
+  hdb_block_core_kernel<<<gw, kHT, 0, s>>>(L.core_sorted, n, nb, L.bmincore);
+  hdb_iota_kernel<<<gp, kHT, 0, s>>>(L.comp, n);
+  count_launch(3);
+  PGS_CHECK_LAUNCH();
+  uint32_t status_h = 0;
+  PGS_CUDA(cudaMemcpyAsync(&status_h, L.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  PGS_CUDA(cudaStreamSynchronize(s));
+  if (status_h) {
+    set_error("pgs_hdb_mst: input contains NaN or infinity");
+    return PGS_ERR_RANGE;
+  }
+  int32_t n_edges = 0, rounds = 0;
+  while (n_edges < n - 1) {
+    if (rounds >= 64) {
+      set_error("pgs_hdb_mst: Boruvka did not converge (%d of %lld edges)", n_edges, (long long)(n - 1));
+      return PGS_ERR_CUDA;
+    }
+    hdb_round_init_kernel<<<blocks_for((int64_t)nb * 32), kHT, 0, s>>>(L.comp, n, nb, L.bcomp, L.U, L.E);
+    hdb_search_kernel<D><<<gw, kHT, 0, s>>>(L.P, L.sids, L.core_sorted, L.comp, n, nb, L.blo, L.bhi, L.bmincore,
+                                            L.bcomp, alpha, L.U, L.bestw, L.bestp);
+    hdb_select_kernel<<<gp, kHT, 0, s>>>(L.sids, L.comp, L.bestw, L.bestp, n, L.U, L.E);
+    hdb_merge_kernel<<<gp, kHT, 0, s>>>(L.comp, L.inv, n, L.U, L.E, L.next, L.edge_uv, L.edge_w, L.n_edges);
+    hdb_relabel_kernel<<<gp, kHT, 0, s>>>(L.comp, L.next, n);
+    count_launch(5);
+    PGS_CHECK_LAUNCH();
+    const int32_t before = n_edges;
+    PGS_CUDA(cudaMemcpyAsync(&n_edges, L.n_edges, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    PGS_CUDA(cudaStreamSynchronize(s));
+    ++rounds;
+    if (n_edges == before) {
+      set_error("pgs_hdb_mst: a Boruvka round added no edge");
+      return PGS_ERR_CUDA;
+    }
+  }
+  if (rounds_host) *rounds_host = rounds;
+  const int m = (int)(n - 1);
+  // strict total order (w, min id, max id): stable sort by the packed ids, then by the weight
+  cb = L.cub_bytes;
+  PGS_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_ws, cb, L.edge_uv, L.edge_uv2, L.edge_w, L.edge_w2, m, 0, 64, s));
+  cb = L.cub_bytes;
+  PGS_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_ws, cb, L.edge_w2, w, L.edge_uv2, L.edge_uv, m, 0, 64, s));
+  hdb_unpack_kernel<<<blocks_for(m), kHT, 0, s>>>(L.edge_uv, m, u, v);
+  count_launch();
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+}  // namespace pgs
+
+using namespace pgs;
+
+extern "C" {
+
+size_t pgs_hdb_scratch_bytes(int64_t n, int32_t D) { return hdb_layout(n < 1 ? 1 : n, D < 1 ? 1 : D, nullptr).total; }
+
+int pgs_hdb_mst(const float* X, int64_t n, int32_t D, int32_t min_samples, double alpha, double* core, int32_t* u,
+                int32_t* v, double* w, int32_t* rounds_host, void* scratch, size_t scratch_bytes, void* stream) {
+  PGS_CHECK_ARG(n >= 2 && n < (1ll << 31), "need 2 <= n < 2^31 samples");
+  PGS_CHECK_ARG(D >= 1 && D <= 8, "dimension must be in 1..8");
+  PGS_CHECK_ARG(min_samples >= 1 && min_samples <= 32 && min_samples <= n, "min_samples must be in 1..min(32, n)");
+  PGS_CHECK_ARG(alpha > 0.0, "alpha must be positive");
+  PGS_CHECK_ARG(scratch_bytes >= pgs_hdb_scratch_bytes(n, D), "scratch too small");
+  HdbLayout L = hdb_layout(n, D, scratch);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (D) {
+    case 1: return hdb_mst_impl<1>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    case 2: return hdb_mst_impl<2>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    case 3: return hdb_mst_impl<3>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    case 4: return hdb_mst_impl<4>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    case 5: return hdb_mst_impl<5>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    case 6: return hdb_mst_impl<6>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    case 7: return hdb_mst_impl<7>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+    default: return hdb_mst_impl<8>(X, n, min_samples, alpha, core, u, v, w, rounds_host, L, s);
+  }
+}
+
+}  // extern "C"
