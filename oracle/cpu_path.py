@@ -141,3 +141,67 @@ def resolve_cfg(cfg, input_nc):
         return o
 
     return ev(cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole step on the CPU: heads, losses, clustering  (reference: models/panoptic/PointGroup3heads.py:101-157,
+# 552-639; core/losses/panoptic_losses.py:7-23,203-343) -- used as the parity oracle of the model-level tests
+# and as the CPU arm that bench.py times next to the GPU path.
+# ------------------------------------------------------------------------------------------------
+def heads_forward(sd, feats, training=True, has_offset=True, has_embed=True):
+    sem = torch.log_softmax(mlp_head(feats, sd, "Semantic", training), dim=-1)
+    off = mlp_head(feats, sd, "Offset", training) if has_offset else None
+    emb = mlp_head(feats, sd, "Embed", training) if has_embed else None
+    return sem, off, emb
+
+
+def offset_loss_ref(pred, gt, n_inst):
+    """panoptic_losses.py:7-23."""
+    norm = (pred - gt).abs().sum(-1).sum() / (n_inst + 1e-6)
+    g = gt / (gt.norm(dim=1, keepdim=True) + 1e-8)
+    p = pred / (pred.norm(dim=1, keepdim=True) + 1e-8)
+    return norm, (-(g * p).sum(-1)).sum() / (n_inst + 1e-6)
+
+
+def discriminative_loss_ref(emb, inst, batch, delta_v=0.5, delta_d=1.5, reg=0.001):
+    """panoptic_losses.py:203-343, written per scene / per instance with explicit python loops."""
+    totals = []
+    for s in torch.unique(batch):
+        e, l = emb[batch == s], inst[batch == s]
+        ids = torch.unique(l)
+        mus, l_var = [], 0.0
+        for i in ids:
+            pts = e[l == i]
+            mu = pts.sum(0) / (pts.shape[0] + 1e-8)
+            mus.append(mu)
+            l_var = l_var + (torch.clamp((pts - mu).abs().sum(1) - delta_v, min=0.0) ** 2).sum() / (pts.shape[0] + 1e-8)
+        k = len(mus)
+        l_var = l_var / k
+        l_dist = 0.0
+        if k > 1:
+            acc = 0.0
+            for a in range(k):
+                for b in range(k):
+                    if a != b:
+                        acc = acc + torch.clamp(2 * delta_d - (mus[a] - mus[b]).abs().sum(), min=0.0) ** 2
+            l_dist = acc / (k * (k - 1))
+        l_reg = sum(m.abs().sum() for m in mus) / k
+        totals.append(l_var + l_dist + reg * l_reg)
+    return sum(totals) / len(totals)
+
+
+def step_loss(sd, cfg, batch, weights, training=True, has_offset=True, has_embed=True):
+    """Forward + the epoch <= prepare_epoch loss of PointGroup3heads._compute_loss on CPU tensors.
+    `batch`: object with x, coords, batch, y, instance_labels, instance_mask, vote_label (CPU torch tensors)."""
+    coords = np.concatenate([batch.batch.numpy()[:, None], batch.coords.numpy()], 1).astype(np.int32)
+    feats = unet_forward(sd, cfg, batch.x, coords, training=training, prefix="Backbone.")
+    sem, off, emb = heads_forward(sd, feats, training, has_offset, has_embed)
+    loss = weights["semantic"] * F.nll_loss(sem, batch.y.long(), ignore_index=-1)
+    im = batch.instance_mask
+    if has_offset:
+        a, b = offset_loss_ref(off[im], batch.vote_label[im], im.sum())
+        loss = loss + weights["offset_norm_loss"] * a + weights["offset_dir_loss"] * b
+    if has_embed:
+        loss = loss + weights["embedding_loss"] * discriminative_loss_ref(emb[im], batch.instance_labels[im],
+                                                                          batch.batch[im])
+    return loss, sem, off, emb

@@ -164,3 +164,38 @@ def region_grow(pos, labels, batch, ignore_labels=[], nsample=16, radius=0.02, m
     members = members[order]
     _, counts = torch.unique_consecutive(key[order], return_counts=True)
     return list(torch.split(members, counts.tolist()))
+
+
+def instance_iou(instance_idx: List[torch.Tensor], instance_labels: torch.Tensor, batch=None) -> torch.Tensor:
+    """IoU of every proposal against every ground-truth instance (tpk signature; reference call sites:
+    torch_points3d/core/losses/panoptic_losses.py:37, every panoptic tracker).
+    instance_labels: 0 = no instance, 1..M per scene.  -> f32 [n_proposals, sum_s M_s], scenes in order.
+    Tensor-op formulation (the CUDA kernel for this row is SURVEY 8f #3, "next")."""
+    dev = instance_labels.device
+    if batch is None:
+        batch = torch.zeros_like(instance_labels)
+    n_prop = len(instance_idx)
+    nb = int(batch.max()) + 1 if batch.numel() else 0
+    per_scene = torch.zeros(nb, dtype=torch.long, device=dev).index_reduce_(
+        0, batch, instance_labels, "amax", include_self=True) if nb else torch.zeros(0, dtype=torch.long, device=dev)
+    offs = torch.cumsum(per_scene, 0) - per_scene
+    total = int(per_scene.sum()) if nb else 0
+    ious = torch.zeros((n_prop, total), dtype=torch.float32, device=dev)
+    if n_prop == 0 or total == 0:
+        return ious
+    gid = torch.where(instance_labels > 0, offs[batch] + instance_labels - 1, torch.full_like(instance_labels, -1))
+    gt_size = torch.bincount(gid[gid >= 0], minlength=total).float()
+    sizes = torch.tensor([c.shape[0] for c in instance_idx], device=dev)
+    flat = torch.cat(instance_idx)
+    pid = torch.repeat_interleave(torch.arange(n_prop, device=dev), sizes)
+    g = gid[flat]
+    ok = g >= 0
+    inter = torch.zeros(n_prop * total, dtype=torch.float32, device=dev)
+    inter.index_add_(0, pid[ok] * total + g[ok], torch.ones(int(ok.sum()), device=dev))
+    inter = inter.view(n_prop, total)
+    # a proposal only competes with the instances of its own scene
+    scene_of_prop = batch[torch.stack([c[0] for c in instance_idx])]
+    scene_of_gt = torch.repeat_interleave(torch.arange(nb, device=dev), per_scene)
+    same = scene_of_prop.unsqueeze(1) == scene_of_gt.unsqueeze(0)
+    union = sizes.float().unsqueeze(1) + gt_size.unsqueeze(0) - inter
+    return torch.where(same, inter / union, torch.zeros_like(inter))
