@@ -250,15 +250,36 @@ def cat(*tensors):
 # --------------------------------------------------------------------------------------------
 # convolution
 # --------------------------------------------------------------------------------------------
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, flops) per conv launch
+PROFILE = None
+
+
+def conv_algorithmic_bytes(n_in, n_out, K, c_in, c_out, has_table):
+    """Compulsory HBM bytes of one gather-GEMM launch (DESIGN.md "conv roofline"): read every input row once,
+    write every output row once, read the weights once, read the gather table once."""
+    return 4 * (n_in * c_in + n_out * c_out) + 4 * K * c_in * c_out + (4 * K * n_out if has_table else 0)
+
+
 def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
     """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed)."""
     lib = _lib.load()
     K = W3.shape[0]
     c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
     Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
                            ptr(Y), stream_ptr()))
+    if PROFILE is not None:
+        e1.record()
+        pairs = int((nbr >= 0).sum()) if (nbr is not None and PROFILE_COUNT_PAIRS) else (n_q if nbr is None else 0)
+        PROFILE.append((e0, e1, conv_algorithmic_bytes(X.shape[0], n_q, K, c_in, c_out, nbr is not None),
+                        2 * pairs * c_in * c_out, (X.shape[0], n_q, K, c_in, c_out)))
     return Y
+
+
+PROFILE_COUNT_PAIRS = False
 
 
 class _SparseConvFn(torch.autograd.Function):

@@ -176,8 +176,8 @@ def instance_iou(instance_idx: List[torch.Tensor], instance_labels: torch.Tensor
         batch = torch.zeros_like(instance_labels)
     n_prop = len(instance_idx)
     nb = int(batch.max()) + 1 if batch.numel() else 0
-    per_scene = torch.zeros(nb, dtype=torch.long, device=dev).index_reduce_(
-        0, batch, instance_labels, "amax", include_self=True) if nb else torch.zeros(0, dtype=torch.long, device=dev)
+    per_scene = torch.zeros(nb, dtype=torch.long, device=dev).scatter_reduce(
+        0, batch, instance_labels, reduce="amax", include_self=True) if nb else torch.zeros(0, dtype=torch.long, device=dev)
     offs = torch.cumsum(per_scene, 0) - per_scene
     total = int(per_scene.sum()) if nb else 0
     ious = torch.zeros((n_prop, total), dtype=torch.float32, device=dev)
