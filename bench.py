@@ -209,6 +209,22 @@ def run_b200(args):
                 "alg_bytes_per_launch": tot_b / max(len(prof), 1), "avg_launch_ms": tot_ms / max(len(prof), 1),
                 "conv_share_of_step": tot_ms / (ms_dev * args.steps)}
 
+    # per-shape table of the conv launches (evidence for DESIGN.md section 5; not part of the JSON line)
+    try:
+        shapes = {}
+        for p in prof:
+            d = shapes.setdefault(p[4], [0, 0.0, 0])
+            d[0] += 1
+            d[1] += p[0].elapsed_time(p[1])
+            d[2] += p[2]
+        rows = [{"n_in": k[0], "n_out": k[1], "K": k[2], "c_in": k[3], "c_out": k[4], "launches": v[0],
+                 "avg_us": 1e3 * v[1] / v[0], "gbps": v[2] / (v[1] * 1e-3) / 1e9} for k, v in shapes.items()]
+        rows.sort(key=lambda r: -r["avg_us"] * r["launches"])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "conv_shapes.json"), "w"), indent=1)
+    except Exception:
+        pass
+
     # ---- PQ of the product's instance partition against the synthetic ground truth ----
     b0 = make_inputs(seed=(args.steps - 1) % SCENE_POOL, n=n)
     got = [c.cpu().numpy() for c in last_dev[1]]

@@ -110,6 +110,16 @@ int pgs_conv_fwd(const float* X, const float* W, const int32_t* nbr, int64_t n_q
                  int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                  float* Y, void* stream);
 
+/* tcgen05 (5th-generation tensor core) variant of pgs_conv_fwd: same result contract, fp32 in / fp32 out,
+ * 3-pass tf32 hi/lo split with fp32 accumulation in tensor memory.  Supported when
+ * pgs_conv_tc_supported(c_in, c_out) (c_in % 16 == 0, c_out % 16 == 0, 16 <= c_out <= 192).
+ * scratch holds the re-arranged weights (pgs_conv_tc_scratch_bytes). */
+int pgs_conv_tc_supported(int32_t c_in, int32_t c_out);
+size_t pgs_conv_tc_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out);
+int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t n_q,
+                    int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
+                    float* Y, void* scratch, size_t scratch_bytes, void* stream);
+
 /* dW must be zeroed by the caller (accumulates).  in_idx/out_idx/offs (device) from pgs_kmap_pairs
  * of the FORWARD table; max_pairs = max_k (offs[k+1]-offs[k]) (host value, sizes the grid).
  * in_idx == out_idx == offs == NULL: K == 1 identity pairs 0..max_pairs-1. */

@@ -250,6 +250,11 @@ def cat(*tensors):
 # --------------------------------------------------------------------------------------------
 # convolution
 # --------------------------------------------------------------------------------------------
+# "tc": tcgen05 gather-GEMM where the channel counts allow it (csrc/conv_tc.cu), fp32 FFMA kernel otherwise;
+# "ffma": always the FFMA kernel (csrc/conv.cu).  Both are CUDA kernels behind the same C ABI.
+import os as _os
+CONV_IMPL = _os.environ.get("PGS_CONV_IMPL", "tc")
+
 # bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, flops) per conv launch
 PROFILE = None
 
@@ -266,11 +271,19 @@ def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
     K = W3.shape[0]
     c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
     Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
+    use_tc = CONV_IMPL == "tc" and lib.pgs_conv_tc_supported(c_in, c_out)
+    if use_tc:
+        nb = lib.pgs_conv_tc_scratch_bytes(K, c_in, c_out)
+        scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
-                           ptr(Y), stream_ptr()))
+    if use_tc:
+        check(lib.pgs_conv_fwd_tc(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
+                                  ptr(Y), ptr(scratch), nb, stream_ptr()))
+    else:
+        check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
+                               ptr(Y), stream_ptr()))
     if PROFILE is not None:
         e1.record()
         pairs = int((nbr >= 0).sum()) if (nbr is not None and PROFILE_COUNT_PAIRS) else (n_q if nbr is None else 0)
