@@ -271,7 +271,7 @@ def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
     K = W3.shape[0]
     c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
     Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
-    use_tc = CONV_IMPL == "tc" and lib.pgs_conv_tc_supported(c_in, c_out)
+    use_tc = CONV_IMPL == "tc" and K <= 27 and lib.pgs_conv_tc_supported(c_in, c_out)
     if use_tc:
         nb = lib.pgs_conv_tc_scratch_bytes(K, c_in, c_out)
         scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)

@@ -9,7 +9,8 @@ from oracle import sparse_ref as sr
 
 dev = torch.device("cuda:0")
 shapes = [(16, 16), (32, 48), (64, 64), (192, 80), (96, 112), (160, 192)] if len(sys.argv) < 2 else [tuple(map(int, a.split("x"))) for a in sys.argv[1:]]
-coords = _scene(2, n=20000)
+NPTS = int(os.environ.get("NPTS", "20000"))
+coords = _scene(2, n=NPTS, extent=int(40 * (NPTS / 20000) ** 0.5))
 mgr = me.CoordinateManager(torch.from_numpy(coords).to(dev))
 km = mgr.kernel_map(1, 1, 1, 1, 3)
 n = km.n_q
