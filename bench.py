@@ -144,8 +144,11 @@ def run_b200(args):
             return loss, flat, sizes
         return None, clusters, None
 
+    dw_prof = []
+
     def timed(k, e2e, profile=None):
         me.PROFILE = profile
+        me.PROFILE_DW = dw_prof if profile is not None else None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -161,6 +164,7 @@ def run_b200(args):
             dist.barrier()
         t1 = time.time()
         me.PROFILE = None
+        me.PROFILE_DW = None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -222,6 +226,15 @@ def run_b200(args):
         rows.sort(key=lambda r: -r["avg_us"] * r["launches"])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "conv_shapes.json"), "w"), indent=1)
+        shapes = {}
+        for p in dw_prof:
+            d = shapes.setdefault(p[2], [0, 0.0])
+            d[0] += 1
+            d[1] += p[0].elapsed_time(p[1])
+        rows = [{"n_in": k[0], "n_out": k[1], "K": k[2], "c_in": k[3], "c_out": k[4], "launches": v[0],
+                 "avg_us": 1e3 * v[1] / v[0]} for k, v in shapes.items()]
+        rows.sort(key=lambda r: -r["avg_us"] * r["launches"])
+        json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "dw_shapes.json"), "w"), indent=1)
     except Exception:
         pass
 

@@ -129,70 +129,124 @@ __global__ void __launch_bounds__(kConvThreads) conv_fwd_kernel(
   }
 }
 
-// dW[k] (64x64 tile) += sum over a chunk of the pairs of table offset tk
-constexpr int kWT = 64;
-constexpr int kPK = 16;
-constexpr int kPairChunk = 2048;
+// ------------------------------------------------------------------------------------------
+// weight gradient:  dW[k][ci][co] += sum over the pairs (in -> out) of offset k of X[in][ci] * dY[out][co]
+//
+// One CTA owns a run of kDwChunk consecutive pairs of one offset and a TCI x TCO tile of dW[k].  The pair rows
+// (the tile's slice of X[in] and dY[out]) stream through a 3-stage cp.async ring in shared memory, so the bytes
+// in flight do not cost registers (the register-staged predecessor sat at 17 % warp occupancy stalled on the
+// long scoreboard, ncu profiles/r1_dw_warp_ncu.txt; the 64 x 64 tile kernel before it left 15/16 of its threads
+// idle at 16 channels: 570 us per launch whatever the shape).  Compute: lane <-> input channel, registers <-> the
+// TCO output channels; a warp takes every 8th pair of a stage, with 32 / TCI pairs side by side in its sub-groups.
+// Partial tiles are summed across the 8 warps in shared memory and flushed with ONE atomicAdd per element and CTA.
+// Pairs are sorted by output row inside an offset, so the dY reads stream.
+// ------------------------------------------------------------------------------------------
+constexpr int kDwThreads = 256;
+constexpr int kDwChunk = 1024;   // pairs per CTA
+constexpr int kDwSP = 64;        // pairs per pipeline stage
+constexpr int kDwStages = 3;
 
-__global__ void __launch_bounds__(kConvThreads) conv_bwd_weight_kernel(
+__device__ __forceinline__ void dw_cp_async16(void* dst_smem, const void* src, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const uint32_t n = pred ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+template <int TCI, int TCO>
+__global__ void __launch_bounds__(kDwThreads) conv_dw_kernel(
     const float* __restrict__ X, const float* __restrict__ dY, const int32_t* __restrict__ in_idx,
-    const int32_t* __restrict__ out_idx, const int32_t* __restrict__ offs, int64_t n_identity, int K,
-    int mirror, int c_in, int c_out, int tiles_co, float* __restrict__ dW) {
-  __shared__ __align__(16) float Xs[kPK][kWT + 4];
-  __shared__ __align__(16) float Ds[kPK][kWT + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;
-  const int ci0 = (blockIdx.x / tiles_co) * kWT, co0 = (blockIdx.x % tiles_co) * kWT;
+    const int32_t* __restrict__ out_idx, const int32_t* __restrict__ offs, int64_t n_identity, int K, int mirror,
+    int c_in, int c_out, int n_co_tiles, float* __restrict__ dW) {
+  constexpr int G = 32 / TCI;            // pairs side by side in one warp
+  constexpr int XQ = TCI / 4;            // 16-byte chunks per staged X row slice
+  constexpr int DQ = TCO / 4;
+  // dynamic shared memory: [s_in][s_out][xs ring][ds ring]; the reduction buffer aliases the rings afterwards
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  int* s_in = (int*)dw_smem;
+  int* s_out = s_in + kDwChunk;
+  float (*xs)[kDwSP][TCI] = (float (*)[kDwSP][TCI])(s_out + kDwChunk);
+  float (*ds)[kDwSP][TCO] = (float (*)[kDwSP][TCO])(&xs[kDwStages][0][0]);
+  float (*red)[TCI][TCO + 1] = (float (*)[TCI][TCO + 1])(&xs[0][0][0]);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / TCI, ci_l = lane % TCI;
+  const int ci0 = (blockIdx.y / n_co_tiles) * TCI, co0 = (blockIdx.y % n_co_tiles) * TCO;
   const int tk = blockIdx.z;
   const int64_t p_begin = offs ? offs[tk] : 0, p_end = offs ? offs[tk + 1] : n_identity;
-  const int64_t p0 = p_begin + (int64_t)blockIdx.y * kPairChunk;
-  const int64_t p1 = (p0 + kPairChunk < p_end) ? p0 + kPairChunk : p_end;
-  if (p0 >= p1) return;
-  float* dWk = dW + (size_t)(mirror ? (K - 1 - tk) : tk) * c_in * c_out;
+  const int64_t start = p_begin + (int64_t)blockIdx.x * kDwChunk;
+  if (start >= p_end) return;
+  const int n_pairs = (int)((p_end - start < kDwChunk) ? (p_end - start) : kDwChunk);
 
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  for (int64_t pb = p0; pb < p1; pb += kPK) {
-    for (int e = tid; e < kPK * kWT; e += kConvThreads) {
-      const int pp = e / kWT, c = e % kWT;
-      const int64_t p = pb + pp;
-      float xv = 0.f, dv = 0.f;
-      if (p < p1) {
-        const int64_t ri = in_idx ? in_idx[p] : p;
-        const int64_t ro = out_idx ? out_idx[p] : p;
-        if (ci0 + c < c_in) xv = __ldg(X + ri * c_in + ci0 + c);
-        if (co0 + c < c_out) dv = __ldg(dY + ro * c_out + co0 + c);
-      }
-      Xs[pp][c] = xv;
-      Ds[pp][c] = dv;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int pp = 0; pp < kPK; ++pp) {
-      const float4 a = *(const float4*)&Xs[pp][ty * 4];
-      const float4 b = *(const float4*)&Ds[pp][tx * 4];
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    __syncthreads();
+  for (int i = tid; i < n_pairs; i += kDwThreads) {
+    s_in[i] = in_idx ? __ldg(&in_idx[start + i]) : (int)(start + i);
+    s_out[i] = out_idx ? __ldg(&out_idx[start + i]) : (int)(start + i);
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + ty * 4 + i;
-    if (ci >= c_in) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + tx * 4 + j;
-      if (co < c_out) atomicAdd(dWk + (size_t)ci * c_out + co, acc[i][j]);
+  __syncthreads();
+
+  const int n_stages = (n_pairs + kDwSP - 1) / kDwSP;
+  auto issue = [&](int st) {
+    if (st < n_stages) {
+      const int buf = st % kDwStages, p0 = st * kDwSP;
+      for (int e = tid; e < kDwSP * XQ; e += kDwThreads) {
+        const int pp = e / XQ, q = e % XQ;
+        const bool ok = p0 + pp < n_pairs && ci0 + 4 * q < c_in;
+        const int64_t row = ok ? s_in[p0 + pp] : 0;
+        dw_cp_async16(&xs[buf][pp][4 * q], X + row * c_in + ci0 + 4 * q, ok);
+      }
+      for (int e = tid; e < kDwSP * DQ; e += kDwThreads) {
+        const int pp = e / DQ, q = e % DQ;
+        const bool ok = p0 + pp < n_pairs && co0 + 4 * q < c_out;
+        const int64_t row = ok ? s_out[p0 + pp] : 0;
+        dw_cp_async16(&ds[buf][pp][4 * q], dY + row * c_out + co0 + 4 * q, ok);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[TCO];
+#pragma unroll
+  for (int j = 0; j < TCO; ++j) acc[j] = 0.f;
+
+  issue(0);
+  issue(1);
+  for (int st = 0; st < n_stages; ++st) {
+    issue(st + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncthreads();
+    const int buf = st % kDwStages;
+    // warp w takes pair slots w*G + sub, (w + 8)*G + sub, ... of the stage (zero-filled slots add nothing)
+#pragma unroll
+    for (int t = 0; t < kDwSP / (8 * G); ++t) {
+      const int pp = (t * 8 + warp) * G + sub;
+      const float xv = xs[buf][pp][ci_l];
+#pragma unroll
+      for (int j = 0; j < DQ; ++j) {
+        const float4 d = *(const float4*)&ds[buf][pp][4 * j];
+        acc[4 * j + 0] = fmaf(xv, d.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(xv, d.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(xv, d.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(xv, d.w, acc[4 * j + 3]);
+      }
+    }
+    __syncthreads();   // the ring slot is refilled by the issue() of the next iteration
+  }
+  // fold the sub-groups (same ci, different pairs), then the 8 warps, then one atomicAdd per element
+#pragma unroll
+  for (int m = TCI; m < 32; m <<= 1)
+#pragma unroll
+    for (int j = 0; j < TCO; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], m);
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < TCO; ++j) red[warp][ci_l][j] = acc[j];
+  }
+  __syncthreads();
+  float* dWk = dW + (size_t)(mirror ? (K - 1 - tk) : tk) * c_in * c_out;
+  for (int e = tid; e < TCI * TCO; e += kDwThreads) {
+    const int ci = e / TCO, j = e % TCO;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDwThreads / 32; ++w) v += red[w][ci][j];
+    if (ci0 + ci < c_in && co0 + j < c_out) atomicAdd(dWk + (size_t)(ci0 + ci) * c_out + co0 + j, v);
   }
 }
 
@@ -231,10 +285,31 @@ int pgs_conv_bwd_weight(const float* X, const float* dY, const int32_t* in_idx, 
   PGS_CHECK_ARG(offs != nullptr || K == 1, "offs == NULL requires K == 1 (identity pairs)");
   if (max_pairs <= 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int tiles_ci = (c_in + kWT - 1) / kWT, tiles_co = (c_out + kWT - 1) / kWT;
-  const unsigned chunks = (unsigned)((max_pairs + kPairChunk - 1) / kPairChunk);
-  conv_bwd_weight_kernel<<<dim3(tiles_ci * tiles_co, chunks, K), kConvThreads, 0, s>>>(
-      X, dY, in_idx, out_idx, offs, max_pairs, K, mirror, c_in, c_out, tiles_co, dW);
+  PGS_CHECK_ARG(c_in % 4 == 0 && c_out % 4 == 0, "channel counts must be multiples of 4 (16-byte row chunks)");
+  const int tci = (c_in % 32 == 0) ? 32 : (c_in % 16 == 0 ? 16 : 4);
+  const int tco = (c_out % 32 == 0) ? 32 : 16;
+  const int n_ci = (c_in + tci - 1) / tci, n_co = (c_out + tco - 1) / tco;
+  const unsigned gx = (unsigned)((max_pairs + kDwChunk - 1) / kDwChunk);
+  const dim3 grid(gx, n_ci * n_co, K);
+#define PGS_DW(TCI, TCO)                                                                                          \
+  do {                                                                                                            \
+    const size_t ring = (size_t)kDwStages * kDwSP * (TCI + TCO) * 4, redb = (size_t)8 * TCI * (TCO + 1) * 4;       \
+    const size_t sm = (size_t)2 * kDwChunk * 4 + (ring > redb ? ring : redb);                                     \
+    static bool attr = false;                                                                                     \
+    if (!attr) {                                                                                                  \
+      PGS_CUDA(cudaFuncSetAttribute(conv_dw_kernel<TCI, TCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+      attr = true;                                                                                                \
+    }                                                                                                             \
+    conv_dw_kernel<TCI, TCO><<<grid, kDwThreads, sm, s>>>(X, dY, in_idx, out_idx, offs, max_pairs, K, mirror, c_in, c_out, \
+                                                          n_co, dW);                                              \
+  } while (0)
+  if (tci == 32 && tco == 32) PGS_DW(32, 32);
+  else if (tci == 32) PGS_DW(32, 16);
+  else if (tci == 16 && tco == 32) PGS_DW(16, 32);
+  else if (tci == 16) PGS_DW(16, 16);
+  else if (tco == 32) PGS_DW(4, 32);
+  else PGS_DW(4, 16);
+#undef PGS_DW
   count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;

@@ -61,10 +61,8 @@ class KernelMap:
             scratch = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
             check(lib.pgs_kmap_pairs(ptr(self.nbr), self.n_q, self.K, ptr(in_idx), ptr(out_idx), ptr(offs),
                                      ptr(scratch), nb, stream_ptr()))
-            offs_h = offs.cpu()
-            npairs = int(offs_h[-1])
-            max_pairs = int((offs_h[1:] - offs_h[:-1]).max()) if self.K > 0 else 0
-            self._pairs = (in_idx[:npairs].clone(), out_idx[:npairs].clone(), offs, max_pairs)
+            # no host sync: the pair count per offset is bounded by n_q (the dW kernel exits on empty chunks)
+            self._pairs = (in_idx, out_idx, offs, self.n_q)
         return self._pairs
 
 
@@ -293,6 +291,7 @@ def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
 
 
 PROFILE_COUNT_PAIRS = False
+PROFILE_DW = None
 
 
 class _SparseConvFn(torch.autograd.Function):
@@ -321,6 +320,9 @@ class _SparseConvFn(torch.autograd.Function):
             dX = _conv_fwd_raw(dY, W3, nbr_b, X.shape[0], ctx.mirror_b, True)
         if ctx.needs_input_grad[1]:
             dW3 = torch.zeros_like(W3)
+            if PROFILE_DW is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             if ctx.km_f is not None:
                 in_idx, out_idx, offs, max_pairs = ctx.km_f.pairs()
                 check(lib.pgs_conv_bwd_weight(ptr(X), ptr(dY), ptr(in_idx), ptr(out_idx), ptr(offs), max_pairs,
@@ -328,6 +330,9 @@ class _SparseConvFn(torch.autograd.Function):
             else:
                 check(lib.pgs_conv_bwd_weight(ptr(X), ptr(dY), None, None, None, X.shape[0], 1, c_in, c_out, 0,
                                               ptr(dW3), stream_ptr()))
+            if PROFILE_DW is not None:
+                e1.record()
+                PROFILE_DW.append((e0, e1, (X.shape[0], dY.shape[0], K, c_in, c_out)))
             dW = dW3.reshape(W.shape)
         return dX, dW, None, None, None, None, None
 

@@ -25,7 +25,7 @@ raw.pgs_debug_trace(buf)
 t = np.array(buf[:320]).reshape(40, 8)
 m = np.array(buf[2048:2048 + 320]).reshape(40, 8)
 print("n rows", n, "cin", cin, "cout", cout)
-print("producer tid0: [wait, split-store, fence, arrive, refill-loads] period | mma lane: [bar wait, issue+commit] period")
-for i in range(4, 28):
+print("producer tid0: [wait, cvt+tmem st, B store, wait::st, fences+arrive, refill] period | mma lane: [bar wait, issue+commit] period")
+for i in range(3, 13):
     r, q = t[i], m[i]
-    print(i, [int(r[j + 1] - r[j]) for j in range(5)], int(t[i + 1][0] - r[0]), "|", [int(q[1] - q[0]), int(q[2] - q[1])], int(m[i + 1][0] - q[0]))
+    print(i, [int(r[j + 1] - r[j]) for j in range(6)], int(t[i + 1][0] - r[0]), "|", [int(q[1] - q[0]), int(q[2] - q[1])], int(m[i + 1][0] - q[0]))
