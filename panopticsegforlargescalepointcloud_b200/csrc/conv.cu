@@ -129,6 +129,146 @@ __global__ void __launch_bounds__(kConvThreads) conv_fwd_kernel(
   }
 }
 
+__device__ __forceinline__ void dw_cp_async16(void* dst_smem, const void* src, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const uint32_t n = pred ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Small-channel forward / input-gradient kernel (c_out in {16, 32}): output stationary, cp.async ring.
+//
+// Why not the tensor cores here: an M = 128 tcgen05.mma costs >= 97 cycles whatever N (profiles/
+// r1_mma_issue_rate.txt), so at N = 16 the 3-pass tf32 path is MMA-issue bound at 162 instructions per 128-row
+// tile (131 us per 200k-row layer) while the same layer is only ~0.9 GFLOP of fp32 FMA work.
+//
+// One CTA owns 128 output rows.  Per pipeline step (one non-empty kernel offset x one slice of <= 32 input
+// channels) the gathered input rows land in shared memory by 16-byte cp.async (missing neighbours zero-filled
+// by src-size 0) together with the matching [slice x c_out] weight block; thread <-> (row, half of the output
+// channels) keeps c_out / 2 accumulators in registers and reads x by broadcast, w by 16-byte broadcast loads.
+// ------------------------------------------------------------------------------------------
+constexpr int kSfThreads = 256;
+constexpr int kSfM = 128;
+constexpr int kSfCS = 32;       // input-channel slice per step
+constexpr int kSfXS = kSfCS + 4;  // row stride in floats: +16 B so that 8 consecutive rows hit 8 different bank groups
+constexpr int kSfStages = 3;
+constexpr int kSfMaxK = 27;
+
+template <int COUT>
+__global__ void __launch_bounds__(kSfThreads) conv_small_kernel(
+    const float* __restrict__ X, const float* __restrict__ W, const int32_t* __restrict__ nbr, int64_t n_q, int K,
+    int c_in, int mirror, int w_transposed, float* __restrict__ Y) {
+  constexpr int CPT = COUT / 2;            // output channels per thread
+  extern __shared__ __align__(16) uint8_t sf_smem[];
+  float (*xs)[kSfM][kSfXS] = (float (*)[kSfM][kSfXS])sf_smem;                       // [stage][row][ci], padded
+  float (*ws)[kSfCS][COUT] = (float (*)[kSfCS][COUT])(&xs[kSfStages][0][0]);       // [stage][ci][co]
+  __shared__ int idx_all[kSfMaxK][kSfM];
+  __shared__ int klist[kSfMaxK];
+  __shared__ unsigned kmask_s;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kSfM;
+  if (tid == 0) kmask_s = 0u;
+  __syncthreads();
+  {
+    unsigned mine = 0u;
+    for (int e = tid; e < K * kSfM; e += kSfThreads) {
+      const int k = e / kSfM, r = e - k * kSfM;
+      const int64_t row = row0 + r;
+      int v = -1;
+      if (row < n_q) v = nbr ? __ldg(&nbr[(int64_t)k * n_q + row]) : (int)row;
+      idx_all[k][r] = v;
+      if (v >= 0) mine |= 1u << k;
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, sft);
+    if (lane == 0 && mine) atomicOr(&kmask_s, mine);
+  }
+  __syncthreads();
+  int n_off = 0;
+  {
+    const unsigned km = kmask_s;
+    for (int k = 0; k < K; ++k) {
+      const int tk = mirror ? (K - 1 - k) : k;
+      if (km & (1u << tk)) {
+        if (tid == 0) klist[n_off] = k;
+        ++n_off;
+      }
+    }
+  }
+  __syncthreads();
+  const int n_slices = (c_in + kSfCS - 1) / kSfCS;
+  const int total = n_off * n_slices;
+
+  auto issue = [&](int step) {
+    if (step < total) {
+      const int o = step / n_slices, sl = step - o * n_slices;
+      const int k = klist[o];
+      const int tk = mirror ? (K - 1 - k) : k;
+      const int buf = step % kSfStages;
+      const int c0 = sl * kSfCS;
+      const int cw = (c_in - c0 < kSfCS) ? (c_in - c0) : kSfCS;   // multiple of 4
+      const int xq = cw / 4;
+      for (int e = tid; e < kSfM * xq; e += kSfThreads) {
+        const int r = e / xq, q = e - r * xq;
+        const int src = idx_all[tk][r];
+        dw_cp_async16(&xs[buf][r][4 * q], X + (size_t)(src < 0 ? 0 : src) * c_in + c0 + 4 * q, src >= 0);
+      }
+      if (!w_transposed) {   // W [K][c_in][COUT]: rows of the slice are contiguous
+        const float* wk = W + ((size_t)k * c_in + c0) * COUT;
+        for (int e = tid; e < cw * (COUT / 4); e += kSfThreads)
+          dw_cp_async16(&ws[buf][0][0] + 4 * e, wk + 4 * e, true);
+      } else {               // W [K][COUT][c_in]: transpose on the way in (4-byte copies)
+        const float* wk = W + (size_t)k * COUT * c_in + c0;
+        for (int e = tid; e < cw * COUT; e += kSfThreads) {
+          const int co = e / cw, ci = e - co * cw;
+          const uint32_t d = (uint32_t)__cvta_generic_to_shared(&ws[buf][ci][co]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(wk + (size_t)co * c_in + ci) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int r = tid >> 1, ch = (tid & 1) * CPT;
+  float acc[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+
+  issue(0);
+  issue(1);
+  for (int step = 0; step < total; ++step) {
+    issue(step + 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncthreads();
+    const int buf = step % kSfStages;
+    const int sl = step % n_slices;
+    const int cw = (c_in - sl * kSfCS < kSfCS) ? (c_in - sl * kSfCS) : kSfCS;
+    for (int c = 0; c < cw; c += 4) {
+      const float4 xv = *(const float4*)&xs[buf][r][c];
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) {
+          const float4 w = *(const float4*)&ws[buf][c + t][ch + 4 * j];
+          acc[4 * j + 0] = fmaf(xa[t], w.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(xa[t], w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(xa[t], w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(xa[t], w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int64_t row = row0 + r;
+  if (row < n_q) {
+    float4* y = (float4*)(Y + (size_t)row * COUT + ch);
+#pragma unroll
+    for (int j = 0; j < CPT / 4; ++j) y[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // weight gradient:  dW[k][ci][co] += sum over the pairs (in -> out) of offset k of X[in][ci] * dY[out][co]
 //
@@ -146,11 +286,6 @@ constexpr int kDwChunk = 1024;   // pairs per CTA
 constexpr int kDwSP = 64;        // pairs per pipeline stage
 constexpr int kDwStages = 3;
 
-__device__ __forceinline__ void dw_cp_async16(void* dst_smem, const void* src, bool pred) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-  const uint32_t n = pred ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
-}
 
 template <int TCI, int TCO>
 __global__ void __launch_bounds__(kDwThreads) conv_dw_kernel(
@@ -262,6 +397,23 @@ int pgs_conv_fwd(const float* X, const float* W, const int32_t* nbr, int64_t n_q
   PGS_CHECK_ARG(nbr != nullptr || K == 1, "nbr == NULL requires K == 1");
   if (n_q == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if ((c_out == 16 || c_out == 32) && c_in % 4 == 0 && K <= kSfMaxK) {
+    const unsigned g = (unsigned)((n_q + kSfM - 1) / kSfM);
+    const size_t sm = (size_t)kSfStages * (kSfM * kSfXS + kSfCS * c_out) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      PGS_CUDA(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      PGS_CUDA(cudaFuncSetAttribute(conv_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    if (c_out == 16)
+      conv_small_kernel<16><<<g, kSfThreads, sm, s>>>(X, W, nbr, n_q, K, c_in, mirror, w_transposed, Y);
+    else
+      conv_small_kernel<32><<<g, kSfThreads, sm, s>>>(X, W, nbr, n_q, K, c_in, mirror, w_transposed, Y);
+    count_launch();
+    PGS_CHECK_LAUNCH();
+    return PGS_OK;
+  }
   const unsigned gx = (unsigned)((n_q + kTM - 1) / kTM);
   if (c_out <= 16) {
     conv_fwd_kernel<16><<<dim3(gx, 1), kConvThreads, 0, s>>>(X, W, nbr, n_q, K, c_in, c_out, mirror,

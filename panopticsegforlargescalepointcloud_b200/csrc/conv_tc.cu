@@ -693,7 +693,7 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t 
     const uint32_t cols = tmem_cols_for(2 * c_out);
     // few row tiles: spread the kernel offsets of a tile over several CTAs (partial tiles meet in Y by atomicAdd)
     int ksplit = 1;
-    if (K > 1 && gx * 2 <= (unsigned)kNumSM) {
+    if (K > 1 && gx * 2 <= (unsigned)kNumSM) {   // (splitting mid-size layers too measured slower: atomics + memset)
       ksplit = (int)((2 * kNumSM) / gx);
       if (ksplit > 9) ksplit = 9;
     }

@@ -252,6 +252,7 @@ def cat(*tensors):
 # "ffma": always the FFMA kernel (csrc/conv.cu).  Both are CUDA kernels behind the same C ABI.
 import os as _os
 CONV_IMPL = _os.environ.get("PGS_CONV_IMPL", "tc")
+SMALL_COUT = int(_os.environ.get("PGS_SMALL_COUT", "0"))  # measured: the tensor-core path wins even at 16 channels
 
 # bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, flops) per conv launch
 PROFILE = None
@@ -269,7 +270,8 @@ def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
     K = W3.shape[0]
     c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
     Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
-    use_tc = CONV_IMPL == "tc" and K <= 27 and lib.pgs_conv_tc_supported(c_in, c_out)
+    # c_out <= SMALL_COUT would take the cp.async FFMA kernel of pgs_conv_fwd instead (198 us vs 131 us at 16->16 x 200k: off)
+    use_tc = CONV_IMPL == "tc" and K <= 27 and c_out > SMALL_COUT and lib.pgs_conv_tc_supported(c_in, c_out)
     if use_tc:
         nb = lib.pgs_conv_tc_scratch_bytes(K, c_in, c_out)
         scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
