@@ -188,6 +188,8 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(lt)
     if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (sparse conv gather-GEMM, fwd and bwd-input launches) ----
@@ -262,6 +264,9 @@ def run_b200(args):
             out["pq"]["cpu"] = out["cpu_baseline"]["pq_sample"]
             out["pq"]["matched"] = out["cpu_baseline"]["pq_sample"] == pq
     print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------

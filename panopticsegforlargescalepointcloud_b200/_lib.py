@@ -92,7 +92,14 @@ def check(rc):
         raise PgsError(load().pgs_last_error().decode())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """Current CUDA stream of the current device as a void* (torch.cuda.current_stream() costs ~17 us per call in
+    Python; the raw getter ~0.3 us -- it is called for every kernel launch)."""
+    if _raw_stream is not None:
+        return c_void_p(_raw_stream(torch.cuda.current_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
