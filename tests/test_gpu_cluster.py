@@ -126,3 +126,26 @@ def test_region_grow_scene_shape(cuda_device):
                           torch.from_numpy(s.batch).to(cuda_device), ignore_labels=ignore, radius=0.3,
                           min_cluster_size=10)
     _check_partition(got, want)
+
+
+def test_region_grow_full_size_c2(cuda_device):
+    """BASELINE configs[1] size: 200k-voxel NPM3D-shape cylinder, shifted coordinates, nsample=200, r=0.18 --
+    the C grid oracle still finishes in seconds, so this is exact partition parity at the benchmark size."""
+    tpk = _tpk()
+    from panopticsegforlargescalepointcloud_b200 import scenes
+    s = scenes.make_scene("urban", 200000, 0.12, 16.0, seed=0)
+    off, _, logits = scenes.synthetic_head_outputs(s, seed=0)
+    shifted = (s.pos + off).astype(np.float32)
+    pred = logits.argmax(1)
+    ignore = [-1] + list(scenes.stuff_classes("urban"))
+    want = tpk_ref.region_grow(shifted, pred, s.batch, ignore, 200, 0.18, 10, method="grid")
+    got = tpk.region_grow(torch.from_numpy(shifted).to(cuda_device), torch.from_numpy(pred).to(cuda_device),
+                          torch.from_numpy(s.batch).to(cuda_device), ignore_labels=ignore, nsample=200, radius=0.18,
+                          min_cluster_size=10)
+    assert len(want) >= 40
+    _check_partition(got, want)
+    # size-independent properties: clusters are disjoint, single-class, at least min_cluster_size
+    allm = torch.cat(got)
+    assert allm.unique().numel() == allm.numel()
+    for c in got:
+        assert c.numel() >= 10 and len(set(pred[c.cpu().numpy()])) == 1

@@ -119,3 +119,37 @@ def test_scaling_property_20k(cuda_device):
     ref = mst_from_data_matrix(X.astype(np.float64), core, DistanceMetric.get_metric("euclidean"), 1.0)
     assert np.array_equal(np.sort(ref["distance"]), w)
     assert len(set(lab) - {-1}) >= 30
+
+
+def test_c3_shape_embeddings_100k(cuda_device):
+    """FOR-instance-shaped case (configs[2], reduced to 100k thing points so the test stays short): synthetic 5-D
+    embeddings of a forest cylinder.  Size-independent properties: spanning tree, sorted weights, w >= cores,
+    every recovered cluster is dominated by one ground-truth tree."""
+    hdb = _hdb()
+    from panopticsegforlargescalepointcloud_b200 import scenes
+    s = scenes.make_scene("forest", 120000, 0.06, 8.0, seed=2)
+    _, emb, _ = scenes.synthetic_head_outputs(s, seed=2)
+    thing = s.instance_mask
+    X = emb[thing][:100000]
+    inst = s.instance_labels[thing][:100000]
+    m = hdb.HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006)
+    lab = m.fit_predict(torch.from_numpy(X).to(cuda_device)).cpu().numpy()
+    u, v, w = (t.cpu().numpy() for t in m.mst_)
+    core = m.core_distances_.cpu().numpy()
+    assert len(w) == len(X) - 1 and np.all(np.diff(w) >= 0) and np.all(u < v)
+    assert np.all(w >= np.maximum(core[u], core[v]))
+    parent = np.arange(len(X))
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+    for a, b in zip(u, v):
+        ra, rb = find(a), find(b)
+        assert ra != rb
+        parent[ra] = rb
+    ids = [l for l in np.unique(lab) if l >= 0]
+    assert len(ids) >= 5
+    pure = [np.bincount(inst[lab == l]).max() / (lab == l).sum() for l in ids]
+    assert np.mean(pure) > 0.95
+    assert m.boruvka_rounds_ <= 32
