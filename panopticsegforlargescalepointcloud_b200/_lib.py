@@ -54,6 +54,9 @@ SIGNATURES = {
 }
 
 
+c_void_p = ctypes.c_void_p
+
+
 class PgsError(RuntimeError):
     pass
 

@@ -28,6 +28,7 @@ import torch.nn as nn
 from . import hdbscan as _hdbscan
 from . import losses as L
 from . import tpk
+from . import me as _me
 from .backbone import Minkowski
 
 IGNORE_LABEL = -1
@@ -222,6 +223,7 @@ class BaseModel(nn.Module):
         self.forward(epoch=epoch, step=step, is_training=True)
         self._optimizer.zero_grad(set_to_none=False)
         self.backward(epoch)
+        _me.join_side_stream()   # weight-gradient kernels run on a side stream (me.DW_DIRECT)
         if self._grad_hook is not None:
             self._grad_hook()
         if self._grad_clip > 0:
