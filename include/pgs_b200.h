@@ -201,6 +201,22 @@ int pgs_hdb_labels_host(const int32_t* u_host, const int32_t* v_host, const doub
                         int32_t min_cluster_size, double cluster_selection_epsilon,
                         int32_t* labels_host, int32_t* n_clusters_host);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused BatchNorm (+ ReLU) on a feature matrix  (replaces ME.MinkowskiBatchNorm [+ ME.MinkowskiReLU];
+ *                    reference: modules/MinkowskiEngine/api_modules.py:40-41,53-54,269-270)
+ * X, Y, dY, dX fp32 [n, C] row-major, C % 4 == 0.  nn.BatchNorm1d semantics: batch statistics over all rows
+ * (biased variance) in training, running estimates in eval; running_var gets the unbiased variance.
+ * sums: fp64 [2C] scratch.  save_mean / save_invstd: fp32 [C], written by forward, read by backward.
+ * relu != 0 fuses max(., 0) into the forward and its mask (Y > 0) into the backward.
+ * dweight / dbias receive sum(g * xhat) / sum(g) (overwritten, not accumulated).
+ * ------------------------------------------------------------------------------------------ */
+int pgs_bn_forward(const float* X, int64_t n, int32_t C, const float* weight, const float* bias,
+                   float* running_mean, float* running_var, int32_t training, float momentum, float eps,
+                   int32_t relu, double* sums, float* save_mean, float* save_invstd, float* Y, void* stream);
+int pgs_bn_backward(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
+                    const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, double* sums,
+                    float* dX, float* dweight, float* dbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

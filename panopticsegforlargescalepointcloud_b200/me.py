@@ -162,6 +162,8 @@ class SparseTensor:
             coordinate_manager = CoordinateManager(coordinates)
             tensor_stride = 1
         self._F = features
+        self._lazy = None   # set by MinkowskiBatchNorm: callable(relu: bool) -> features (BN evaluated on demand,
+        #                     so that a following MinkowskiReLU can fuse into the same kernel)
         self.coordinate_manager = coordinate_manager
         self.tensor_stride = int(tensor_stride)
         n_map = coordinate_manager.get_map(self.tensor_stride).n
@@ -171,6 +173,11 @@ class SparseTensor:
     # ME-compatible accessors
     @property
     def F(self):
+        if self._lazy is not None:
+            self._F = self._lazy(False)
+            self._lazy = None
+        if self._F is None:
+            raise RuntimeError("this BatchNorm output was consumed by a fused ReLU; use the ReLU's output")
         return self._F
 
     features = F
@@ -187,7 +194,7 @@ class SparseTensor:
 
     @property
     def device(self):
-        return self._F.device
+        return self._F.device   # (_F of a deferred tensor is the BN input: same device / dtype / shape)
 
     @property
     def dtype(self):
@@ -210,6 +217,12 @@ class SparseTensor:
     def _like(self, F):
         return SparseTensor(F, coordinate_manager=self.coordinate_manager, tensor_stride=self.tensor_stride)
 
+    def _deferred(self, fn):
+        """Same map, features = fn(relu) evaluated on first use (see MinkowskiBatchNorm / MinkowskiReLU)."""
+        t = SparseTensor(self._F, coordinate_manager=self.coordinate_manager, tensor_stride=self.tensor_stride)
+        t._lazy = fn
+        return t
+
     def _check_same_map(self, other):
         if not isinstance(other, SparseTensor):
             return
@@ -218,17 +231,17 @@ class SparseTensor:
 
     def __add__(self, other):
         self._check_same_map(other)
-        return self._like(self._F + (other._F if isinstance(other, SparseTensor) else other))
+        return self._like(self.F + (other.F if isinstance(other, SparseTensor) else other))
 
     __radd__ = __add__
 
     def __sub__(self, other):
         self._check_same_map(other)
-        return self._like(self._F - (other._F if isinstance(other, SparseTensor) else other))
+        return self._like(self.F - (other.F if isinstance(other, SparseTensor) else other))
 
     def __mul__(self, other):
         self._check_same_map(other)
-        return self._like(self._F * (other._F if isinstance(other, SparseTensor) else other))
+        return self._like(self.F * (other.F if isinstance(other, SparseTensor) else other))
 
     def __repr__(self):
         return "SparseTensor(n=%d, c=%d, tensor_stride=%d, device=%s)" % (
@@ -495,16 +508,82 @@ class MinkowskiNetwork(nn.Module):
         self.D = D
 
 
+class _BnFn(torch.autograd.Function):
+    """Fused BatchNorm (+ ReLU) through pgs_bn_forward / pgs_bn_backward."""
+
+    @staticmethod
+    def forward(ctx, X, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+        lib = _lib.load()
+        X = X.contiguous()
+        n, C = X.shape
+        dev = X.device
+        Y = torch.empty_like(X)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        stats = torch.empty((2, C), dtype=torch.float32, device=dev)
+        check(lib.pgs_bn_forward(ptr(X), n, C, ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var),
+                                 int(training), float(momentum), float(eps), int(relu), ptr(sums), ptr(stats[0]),
+                                 ptr(stats[1]), ptr(Y), stream_ptr()))
+        ctx.save_for_backward(X, Y if relu else None, weight, stats)
+        ctx.training, ctx.relu = bool(training), bool(relu)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        lib = _lib.load()
+        X, Y, weight, stats = ctx.saved_tensors
+        dY = dY.contiguous()
+        n, C = X.shape
+        dX = torch.empty_like(X)
+        sums = torch.empty(2 * C, dtype=torch.float64, device=X.device)
+        dwb = torch.empty((2, C), dtype=torch.float32, device=X.device)
+        check(lib.pgs_bn_backward(ptr(X), ptr(Y), ptr(dY), n, C, ptr(weight), ptr(stats[0]), ptr(stats[1]),
+                                  int(ctx.training), int(ctx.relu), ptr(sums), ptr(dX), ptr(dwb[0]), ptr(dwb[1]),
+                                  stream_ptr()))
+        dw = dwb[0] if (weight is not None and ctx.needs_input_grad[1]) else None
+        db = dwb[1] if ctx.needs_input_grad[2] else None
+        return dX, dw, db, None, None, None, None, None, None
+
+
+BN_IMPL = _os.environ.get("PGS_BN_IMPL", "fused")   # "torch": nn.BatchNorm1d kernels + separate ReLU
+
+
 class MinkowskiBatchNorm(nn.Module):
-    """nn.BatchNorm1d over all active rows; the inner module is `.bn` (checkpoint key contract)."""
+    """nn.BatchNorm1d over all active rows; the inner module is `.bn` (checkpoint key contract).  The arithmetic
+    runs in the fused kernels of csrc/norm.cu (and absorbs a directly following MinkowskiReLU)."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
         super().__init__()
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
                                  track_running_stats=track_running_stats)
 
+    @property
+    def momentum(self):   # core/schedulers/bn_schedulers.py pokes .momentum on BN modules
+        return self.bn.momentum
+
+    @momentum.setter
+    def momentum(self, v):
+        self.bn.momentum = v
+
+    def _fused_ok(self, F):
+        bn = self.bn
+        return (BN_IMPL == "fused" and F.is_cuda and F.dtype == torch.float32 and F.shape[1] % 4 == 0
+                and F.shape[1] <= 1024 and F.shape[0] > 0 and bn.momentum is not None
+                and (bn.training or bn.track_running_stats))
+
     def forward(self, x: SparseTensor):
-        return x._like(self.bn(x.F))
+        F = x.F
+        if not self._fused_ok(F):
+            return x._like(self.bn(F))
+        bn = self.bn
+        training = bn.training or not bn.track_running_stats
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+
+        def run(relu):
+            return _BnFn.apply(F, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                               bn.running_var if bn.track_running_stats else None, training, bn.momentum, bn.eps, relu)
+
+        return x._deferred(run)
 
 
 class MinkowskiInstanceNorm(nn.Module):
@@ -523,6 +602,11 @@ class MinkowskiReLU(nn.Module):
         super().__init__()
 
     def forward(self, x: SparseTensor):
+        if x._lazy is not None:          # BN -> ReLU: one fused kernel pair
+            fn, x._lazy = x._lazy, None
+            y = x._like(fn(True))
+            x._F = None          # the un-rectified BN output was never materialised
+            return y
         return x._like(torch.relu(x.F))
 
 

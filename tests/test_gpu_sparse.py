@@ -275,3 +275,41 @@ def test_full_size_properties(cuda_device):
     # every fine row maps into exactly one coarse row through exactly one of the 8 "child" offsets
     child = torch.stack([up[k] for k in (13, 14, 16, 17, 22, 23, 25, 26)])
     assert coarse.n < n and int((child >= 0).sum(0).min()) == 1 and int((child >= 0).sum(0).max()) == 1
+
+
+@pytest.mark.parametrize("C,n,relu,training", [(16, 5000, True, True), (48, 777, False, True), (96, 64, True, True),
+                                               (192, 3, True, True), (32, 4000, True, False), (112, 50, False, False)])
+def test_fused_batchnorm_matches_torch(cuda_device, C, n, relu, training):
+    """csrc/norm.cu vs nn.BatchNorm1d (+ ReLU): outputs, input / affine gradients, running statistics."""
+    me = _me()
+    torch.manual_seed(C + n)
+    dev = cuda_device
+    coords = torch.cat([torch.zeros(n, 1, dtype=torch.int32), torch.arange(n, dtype=torch.int32).unsqueeze(1),
+                        torch.zeros(n, 2, dtype=torch.int32)], 1).to(dev)
+    mgr = me.CoordinateManager(coords)
+    x = (torch.randn(n, C, device=dev) * 2 + 0.5)
+    a = me.MinkowskiBatchNorm(C).to(dev)
+    ref = torch.nn.BatchNorm1d(C).to(dev)
+    with torch.no_grad():
+        for m in (a.bn, ref):
+            m.weight.copy_(torch.linspace(0.5, 1.5, C)); m.bias.copy_(torch.linspace(-0.2, 0.3, C))
+            m.running_mean.copy_(torch.linspace(-0.1, 0.1, C)); m.running_var.copy_(torch.linspace(0.8, 1.2, C))
+    a.train(training); ref.train(training)
+    xa = x.clone().requires_grad_(True); xr = x.clone().requires_grad_(True)
+    out = a(me.SparseTensor(xa, coordinate_manager=mgr))
+    if relu:
+        out = me.MinkowskiReLU()(out)
+    ya = out.F
+    yr = ref(xr)
+    if relu:
+        yr = torch.relu(yr)
+    g = torch.randn_like(yr)
+    ya.backward(g); yr.backward(g)
+    tol = dict(atol=2e-5, rtol=1e-4)
+    assert torch.allclose(ya, yr, **tol)
+    assert torch.allclose(xa.grad, xr.grad, atol=2e-5 * max(1.0, float(xr.grad.abs().max())), rtol=1e-4)
+    assert torch.allclose(a.bn.weight.grad, ref.weight.grad, atol=1e-4 * max(1.0, float(ref.weight.grad.abs().max())), rtol=1e-4)
+    assert torch.allclose(a.bn.bias.grad, ref.bias.grad, atol=1e-4 * max(1.0, float(ref.bias.grad.abs().max())), rtol=1e-4)
+    assert torch.allclose(a.bn.running_mean, ref.running_mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(a.bn.running_var, ref.running_var, atol=1e-5, rtol=1e-4)
+    assert int(a.bn.num_batches_tracked) == int(ref.num_batches_tracked)
