@@ -120,6 +120,25 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t 
                     int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                     float* Y, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Register-operand tensor-core variant for the narrow layers (mma.sync m16n8k8 tf32, A fragments gathered
+ * straight from global memory, no shared-memory staging of the feature rows): same result contract and the same
+ * 3-pass tf32 hi/lo split as pgs_conv_fwd_tc.  Supported when pgs_conv_mma_supported(c_in, c_out)
+ * (both multiples of 16 in 16..64); nbr must not be NULL.  scratch holds the fragment-ordered hi/lo weights
+ * (pgs_conv_mma_scratch_bytes). */
+int pgs_conv_mma_supported(int32_t c_in, int32_t c_out);
+size_t pgs_conv_mma_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out);
+int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, int64_t n_q,
+                     int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
+                     float* Y, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Few-row variant of pgs_conv_fwd_mma for the coarse U-Net levels (latency bound: a few MFLOP, up to 4 MB of
+ * weights): one warp per (16 rows, 16 output channels, part of the kernel offsets), partial sums meet in Y by
+ * atomicAdd.  Any channel counts that are multiples of 16.  Same scratch as pgs_conv_fwd_mma. */
+int pgs_conv_mma_split_supported(int32_t c_in, int32_t c_out);
+int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, int64_t n_q,
+                           int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
+                           float* Y, void* scratch, size_t scratch_bytes, void* stream);
+
 /* dW must be zeroed by the caller (accumulates).  in_idx/out_idx/offs (device) from pgs_kmap_pairs
  * of the FORWARD table; max_pairs = max_k (offs[k+1]-offs[k]) (host value, sizes the grid).
  * in_idx == out_idx == offs == NULL: K == 1 identity pairs 0..max_pairs-1. */

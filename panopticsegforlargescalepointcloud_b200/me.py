@@ -261,8 +261,10 @@ def cat(*tensors):
 # --------------------------------------------------------------------------------------------
 # convolution
 # --------------------------------------------------------------------------------------------
-# "tc": tcgen05 gather-GEMM where the channel counts allow it (csrc/conv_tc.cu), fp32 FFMA kernel otherwise;
-# "ffma": always the FFMA kernel (csrc/conv.cu).  Both are CUDA kernels behind the same C ABI.
+# "auto": register-operand mma kernel (csrc/conv_mma.cu) for narrow layers with many rows, tcgen05 gather-GEMM
+#         (csrc/conv_tc.cu) where the channel counts allow it, fp32 FFMA kernel (csrc/conv.cu) otherwise;
+# "tc" / "mma": prefer that tensor-core kernel wherever it supports the shape;  "ffma": always the FFMA kernel.
+# All are CUDA kernels behind the same C ABI.
 import os as _os
 CONV_IMPL = _os.environ.get("PGS_CONV_IMPL", "tc")
 SMALL_COUT = int(_os.environ.get("PGS_SMALL_COUT", "0"))  # measured: the tensor-core path wins even at 16 channels
@@ -277,23 +279,55 @@ def conv_algorithmic_bytes(n_in, n_out, K, c_in, c_out, has_table):
     return 4 * (n_in * c_in + n_out * c_out) + 4 * K * c_in * c_out + (4 * K * n_out if has_table else 0)
 
 
+# Rows below which the register-operand mma kernel is not used: few-row layers are latency bound and the tcgen05
+# kernel splits their kernel offsets over CTAs.  (csrc/conv_mma.cu; measured per shape in profiles/)
+MMA_MIN_ROWS = int(_os.environ.get("PGS_MMA_MIN_ROWS", "8192"))
+SPLIT_MAX_ROWS = int(_os.environ.get("PGS_SPLIT_MAX_ROWS", "2048"))
+MMA_MAX_CH = int(_os.environ.get("PGS_MMA_MAX_CH", "64"))
+
+
+def _conv_kernel_choice(lib, K, c_in, c_out, n_q, has_table):
+    """"mma" (register-operand tensor cores, narrow + tall layers), "tc" (tcgen05) or "ffma"."""
+    if CONV_IMPL == "ffma":
+        return "ffma"
+    split_ok = has_table and K <= 27 and lib.pgs_conv_mma_split_supported(c_in, c_out)
+    if split_ok and (CONV_IMPL == "split" or (CONV_IMPL == "auto" and n_q <= SPLIT_MAX_ROWS)):
+        return "split"
+    mma_ok = (has_table and K <= 27 and max(c_in, c_out) <= MMA_MAX_CH and lib.pgs_conv_mma_supported(c_in, c_out))
+    if CONV_IMPL == "mma" and mma_ok:
+        return "mma"
+    if CONV_IMPL == "auto" and mma_ok and n_q >= MMA_MIN_ROWS:
+        return "mma"
+    if K <= 27 and c_out > SMALL_COUT and lib.pgs_conv_tc_supported(c_in, c_out):
+        return "tc"
+    return "ffma"
+
+
 def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
     """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed)."""
     lib = _lib.load()
     K = W3.shape[0]
     c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
     Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
-    # c_out <= SMALL_COUT would take the cp.async FFMA kernel of pgs_conv_fwd instead (198 us vs 131 us at 16->16 x 200k: off)
-    use_tc = CONV_IMPL == "tc" and K <= 27 and c_out > SMALL_COUT and lib.pgs_conv_tc_supported(c_in, c_out)
-    if use_tc:
+    kind = _conv_kernel_choice(lib, K, c_in, c_out, n_q, nbr is not None)
+    if kind == "tc":
         nb = lib.pgs_conv_tc_scratch_bytes(K, c_in, c_out)
+        scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
+    elif kind in ("mma", "split"):
+        nb = lib.pgs_conv_mma_scratch_bytes(K, c_in, c_out)
         scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if use_tc:
+    if kind == "tc":
         check(lib.pgs_conv_fwd_tc(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
                                   ptr(Y), ptr(scratch), nb, stream_ptr()))
+    elif kind == "mma":
+        check(lib.pgs_conv_fwd_mma(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
+                                   ptr(Y), ptr(scratch), nb, stream_ptr()))
+    elif kind == "split":
+        check(lib.pgs_conv_fwd_mma_split(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror),
+                                         int(w_transposed), ptr(Y), ptr(scratch), nb, stream_ptr()))
     else:
         check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
                                ptr(Y), stream_ptr()))
@@ -301,7 +335,7 @@ def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
         e1.record()
         pairs = int((nbr >= 0).sum()) if (nbr is not None and PROFILE_COUNT_PAIRS) else (n_q if nbr is None else 0)
         PROFILE.append((e0, e1, conv_algorithmic_bytes(X.shape[0], n_q, K, c_in, c_out, nbr is not None),
-                        2 * pairs * c_in * c_out, (X.shape[0], n_q, K, c_in, c_out)))
+                        2 * pairs * c_in * c_out, (X.shape[0], n_q, K, c_in, c_out), kind))
     return Y
 
 
