@@ -209,22 +209,28 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "pgs::conv_tc_kernel (tcgen05 gather-GEMM; forward + input-gradient launches)",
+    roofline = {"bound": "hbm", "kernel": "sparse-conv gather-GEMM launches, forward + input-gradient (pgs::conv_mma_kernel "
+                "[register-operand tf32 mma, narrow layers], pgs::conv_tc_kernel [tcgen05], pgs::conv_mma_split_kernel "
+                "[few-row layers]); time per kernel kind in by_kernel_ms",
                 "achieved": achieved,
                 "peak": peak, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "launches": len(prof),
                 "alg_bytes_per_launch": tot_b / max(len(prof), 1), "avg_launch_ms": tot_ms / max(len(prof), 1),
                 "conv_share_of_step": tot_ms / (ms_dev * args.steps)}
+    by_kind = {}
+    for p in prof:
+        by_kind[p[5]] = by_kind.get(p[5], 0.0) + p[0].elapsed_time(p[1])
+    roofline["by_kernel_ms_per_step"] = {k: v / args.steps for k, v in sorted(by_kind.items())}
 
     # per-shape table of the conv launches (evidence for DESIGN.md section 5; not part of the JSON line)
     try:
         shapes = {}
         for p in prof:
-            d = shapes.setdefault(p[4], [0, 0.0, 0])
+            d = shapes.setdefault(p[4] + (p[5],), [0, 0.0, 0])
             d[0] += 1
             d[1] += p[0].elapsed_time(p[1])
             d[2] += p[2]
-        rows = [{"n_in": k[0], "n_out": k[1], "K": k[2], "c_in": k[3], "c_out": k[4], "launches": v[0],
+        rows = [{"n_in": k[0], "n_out": k[1], "K": k[2], "c_in": k[3], "c_out": k[4], "kernel": k[5], "launches": v[0],
                  "avg_us": 1e3 * v[1] / v[0], "gbps": v[2] / (v[1] * 1e-3) / 1e9} for k, v in shapes.items()]
         rows.sort(key=lambda r: -r["avg_us"] * r["launches"])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

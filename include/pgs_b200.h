@@ -110,13 +110,23 @@ int pgs_conv_fwd(const float* X, const float* W, const int32_t* nbr, int64_t n_q
                  int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                  float* Y, void* stream);
 
+/* Occupancy-sorted gather table for the tensor-core conv kernels.  Those kernels skip every (16- or 128-row tile,
+ * kernel offset) pair without a neighbour; rows in arbitrary order leave almost none (a 16-row union has ~26 of 27
+ * offsets although a row has 2..13).  pgs_kmap_row_masks writes the per-offset pair counts (counts[K]) and one
+ * K-bit occupancy mask per row (rarest offset = most significant bit); the caller sorts the masks (stable) to get
+ * `order`, and pgs_kmap_permute writes nbr_sorted[k][r] = nbr[k][order[r]].  Passing (nbr_sorted, order) to a
+ * tensor-core entry point gives bit-identical results to (nbr, NULL): tile row r is output row order[r]. */
+int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* counts, int64_t* masks, void* stream);
+int pgs_kmap_permute(const int32_t* nbr, int64_t n_q, int32_t K, const int32_t* order, int32_t* nbr_sorted,
+                     void* stream);
+
 /* tcgen05 (5th-generation tensor core) variant of pgs_conv_fwd: same result contract, fp32 in / fp32 out,
  * 3-pass tf32 hi/lo split with fp32 accumulation in tensor memory.  Supported when
  * pgs_conv_tc_supported(c_in, c_out) (c_in % 16 == 0, c_out % 16 == 0, 16 <= c_out <= 192).
  * scratch holds the re-arranged weights (pgs_conv_tc_scratch_bytes). */
 int pgs_conv_tc_supported(int32_t c_in, int32_t c_out);
 size_t pgs_conv_tc_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out);
-int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t n_q,
+int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q,
                     int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                     float* Y, void* scratch, size_t scratch_bytes, void* stream);
 
@@ -127,7 +137,7 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t 
  * (pgs_conv_mma_scratch_bytes). */
 int pgs_conv_mma_supported(int32_t c_in, int32_t c_out);
 size_t pgs_conv_mma_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out);
-int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, int64_t n_q,
+int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q,
                      int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                      float* Y, void* scratch, size_t scratch_bytes, void* stream);
 
@@ -135,7 +145,7 @@ int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, int64_t
  * weights): one warp per (16 rows, 16 output channels, part of the kernel offsets), partial sums meet in Y by
  * atomicAdd.  Any channel counts that are multiples of 16.  Same scratch as pgs_conv_fwd_mma. */
 int pgs_conv_mma_split_supported(int32_t c_in, int32_t c_out);
-int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, int64_t n_q,
+int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q,
                            int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                            float* Y, void* scratch, size_t scratch_bytes, void* stream);
 

@@ -47,14 +47,16 @@ SIGNATURES = {
     "pgs_hdb_labels_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p, c_void_p]),
     "pgs_conv_tc_supported": (c_int, [c_int32, c_int32]),
     "pgs_conv_tc_scratch_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
-    "pgs_conv_fwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+    "pgs_conv_fwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                 c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pgs_conv_mma_supported": (c_int, [c_int32, c_int32]),
     "pgs_conv_mma_scratch_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
-    "pgs_conv_fwd_mma": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+    "pgs_conv_fwd_mma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pgs_conv_mma_split_supported": (c_int, [c_int32, c_int32]),
-    "pgs_conv_fwd_mma_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
+    "pgs_kmap_row_masks": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgs_kmap_permute": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgs_conv_fwd_mma_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pgs_bn_forward": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                c_float, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

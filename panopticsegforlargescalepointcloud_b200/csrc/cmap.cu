@@ -154,6 +154,56 @@ __global__ void __launch_bounds__(kThreads) pairs_emit_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Occupancy-sorted gather tables.  The tensor-core conv kernels skip every (16-row tile, kernel offset) pair whose
+// rows have no neighbour at that offset; with rows in arbitrary order almost no pair is empty (each row has 2..13
+// of 27 neighbours but a 16-row union has ~26).  Sorting the rows of a table by their K-bit occupancy mask (rarest
+// offset = most significant bit) makes the rows of a tile share their empty offsets: the union drops to ~11 of 27
+// for the stride-1 maps and to ~2.4 for the transposed (up-sampling) maps, whose masks are parity classes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) kmap_counts_kernel(const int32_t* __restrict__ nbr, int64_t n_q,
+                                                               int32_t* __restrict__ counts) {
+  const int k = blockIdx.y;
+  int c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += (int64_t)gridDim.x * blockDim.x)
+    c += nbr[(int64_t)k * n_q + i] >= 0;
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[k], c);
+}
+
+__global__ void __launch_bounds__(kThreads) kmap_masks_kernel(const int32_t* __restrict__ nbr, int64_t n_q, int K,
+                                                              const int32_t* __restrict__ counts,
+                                                              int64_t* __restrict__ masks) {
+  __shared__ int bitpos[64];
+  if (threadIdx.x < K) {   // position of offset k in the order (count descending, k ascending): commonest -> bit 0
+    const int k = threadIdx.x, ck = counts[k];
+    int pos = 0;
+    for (int j = 0; j < K; ++j) {
+      const int cj = counts[j];
+      pos += (cj > ck) || (cj == ck && j < k);
+    }
+    bitpos[k] = pos;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_q) return;
+  uint64_t m = 0;
+  for (int k = 0; k < K; ++k)
+    if (nbr[(int64_t)k * n_q + i] >= 0) m |= 1ull << bitpos[k];
+  masks[i] = (int64_t)m;
+}
+
+__global__ void __launch_bounds__(kThreads) kmap_permute_kernel(const int32_t* __restrict__ nbr, int64_t n_q,
+                                                                const int32_t* __restrict__ order,
+                                                                int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_q) return;
+  const int k = blockIdx.y;
+  out[(int64_t)k * n_q + i] = nbr[(int64_t)k * n_q + order[i]];
+}
+
 static inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 
 }  // namespace pgs
@@ -254,6 +304,29 @@ int pgs_kmap_pairs(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* in_idx, 
   int rc = exclusive_scan_i32(flags, pos, t, p, s);
   if (rc) return rc;
   pairs_emit_kernel<<<grid_for(t + 1), kThreads, 0, s>>>(nbr, pos, n_q, K, in_idx, out_idx, offs);
+  count_launch();
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* counts, int64_t* masks, void* stream) {
+  PGS_CHECK_ARG(K >= 1 && K <= 63, "kernel volume must be in 1..63");
+  cudaStream_t s = (cudaStream_t)stream;
+  PGS_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * K, s));
+  if (n_q == 0) return PGS_OK;
+  int gx = grid_for(n_q);
+  if (gx > kNumSM * 4) gx = kNumSM * 4;
+  kmap_counts_kernel<<<dim3(gx, K), kThreads, 0, s>>>(nbr, n_q, counts);
+  kmap_masks_kernel<<<grid_for(n_q), kThreads, 0, s>>>(nbr, n_q, K, counts, masks);
+  count_launch(2);
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+int pgs_kmap_permute(const int32_t* nbr, int64_t n_q, int32_t K, const int32_t* order, int32_t* nbr_sorted,
+                     void* stream) {
+  if (n_q == 0) return PGS_OK;
+  kmap_permute_kernel<<<dim3(grid_for(n_q), K), kThreads, 0, (cudaStream_t)stream>>>(nbr, n_q, order, nbr_sorted);
   count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;

@@ -95,9 +95,10 @@ __global__ void __launch_bounds__(256) conv_mma_prep_weights_kernel(const float*
 // WS = 0: weights of one kernel offset staged in shared memory (cp.async double buffer, one barrier per offset)
 // WS = 1: weight fragments read straight from global memory (L1-resident for the small shapes), no barrier
 template <int CIN, int COUT, int MT, int WS>
-__global__ void __launch_bounds__(kMmThreads) conv_mma_kernel(const float* __restrict__ X, const float4* __restrict__ Wf,
+__global__ void __launch_bounds__(kMmThreads, (CIN * COUT <= 32 * 32 ? 2 : 1)) conv_mma_kernel(const float* __restrict__ X, const float4* __restrict__ Wf,
                                                                const int32_t* __restrict__ nbr, int64_t n_q, int K,
-                                                               int mirror, float* __restrict__ Y) {
+                                                               int mirror, const int32_t* __restrict__ order,
+                                                               float* __restrict__ Y) {
   constexpr int R = kMmWarps * 16 * MT;   // rows per CTA
   constexpr int J = CIN / 8, NT = COUT / 8, F4 = CIN / 16;
   constexpr int WSTAGE = J * NT * 32;     // float4 elements of one offset's fragments
@@ -232,15 +233,18 @@ __global__ void __launch_bounds__(kMmThreads) conv_mma_kernel(const float* __res
   // epilogue: lane (g, t) owns channels 16 m + 4 t .. +3 of rows g and g + 8 of each m-tile
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    const int64_t r0 = row0 + warp * 16 * MT + mt * 16 + g, r1 = r0 + 8;
+    const int64_t t0 = row0 + warp * 16 * MT + mt * 16 + g, t1 = t0 + 8;   // rows of the (sorted) table
+    const bool ok0 = t0 < n_q, ok1 = t1 < n_q;
+    const int64_t r0 = (ok0 && order) ? (int64_t)__ldg(&order[t0]) : t0;   // output rows
+    const int64_t r1 = (ok1 && order) ? (int64_t)__ldg(&order[t1]) : t1;
 #pragma unroll
     for (int m = 0; m < NT / 2; ++m) {
       const int c = 16 * m + 4 * t;
-      if (r0 < n_q)
+      if (ok0)
         *(float4*)(Y + (size_t)r0 * COUT + c) =
             make_float4(accm[mt][2 * m][0] + accc[mt][2 * m][0], accm[mt][2 * m][1] + accc[mt][2 * m][1],
                         accm[mt][2 * m + 1][0] + accc[mt][2 * m + 1][0], accm[mt][2 * m + 1][1] + accc[mt][2 * m + 1][1]);
-      if (r1 < n_q)
+      if (ok1)
         *(float4*)(Y + (size_t)r1 * COUT + c) =
             make_float4(accm[mt][2 * m][2] + accc[mt][2 * m][2], accm[mt][2 * m][3] + accc[mt][2 * m][3],
                         accm[mt][2 * m + 1][2] + accc[mt][2 * m + 1][2], accm[mt][2 * m + 1][3] + accc[mt][2 * m + 1][3]);
@@ -261,7 +265,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32) conv_mma_split_kernel(const 
                                                                           const float4* __restrict__ Wf,
                                                                           const int32_t* __restrict__ nbr, int64_t n_q,
                                                                           int K, int c_in, int c_out, int mirror,
-                                                                          int ksplit, int mtiles, float* __restrict__ Y) {
+                                                                          int ksplit, int mtiles,
+                                                                          const int32_t* __restrict__ order,
+                                                                          float* __restrict__ Y) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t item = (int64_t)blockIdx.x * kSplitWarps + (threadIdx.x >> 5);
   const int nchunks = c_out >> 4;
@@ -318,23 +324,26 @@ __global__ void __launch_bounds__(kSplitWarps * 32) conv_mma_split_kernel(const 
     }
   }
   const int c = 16 * nc + 4 * t;
+  const bool ok0 = r0 < n_q, ok1 = r1 < n_q;
+  const int64_t y0 = (ok0 && order) ? (int64_t)__ldg(&order[r0]) : r0;   // output rows
+  const int64_t y1 = (ok1 && order) ? (int64_t)__ldg(&order[r1]) : r1;
   const float o0[4] = {accm[0][0] + accc[0][0], accm[0][1] + accc[0][1], accm[1][0] + accc[1][0], accm[1][1] + accc[1][1]};
   const float o1[4] = {accm[0][2] + accc[0][2], accm[0][3] + accc[0][3], accm[1][2] + accc[1][2], accm[1][3] + accc[1][3]};
   if (ksplit == 1) {
-    if (r0 < n_q) *(float4*)(Y + (size_t)r0 * c_out + c) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-    if (r1 < n_q) *(float4*)(Y + (size_t)r1 * c_out + c) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+    if (ok0) *(float4*)(Y + (size_t)y0 * c_out + c) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+    if (ok1) *(float4*)(Y + (size_t)y1 * c_out + c) = make_float4(o1[0], o1[1], o1[2], o1[3]);
   } else if (touched) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (r0 < n_q) atomicAdd(Y + (size_t)r0 * c_out + c + i, o0[i]);
-      if (r1 < n_q) atomicAdd(Y + (size_t)r1 * c_out + c + i, o1[i]);
+      if (ok0) atomicAdd(Y + (size_t)y0 * c_out + c + i, o0[i]);
+      if (ok1) atomicAdd(Y + (size_t)y1 * c_out + c + i, o1[i]);
     }
   }
 }
 
 template <int CIN, int COUT, int MT, int WS>
-static int launch_mma(const float* X, const float* Wf, const int32_t* nbr, int64_t n_q, int K, int mirror, float* Y,
-                      cudaStream_t s) {
+static int launch_mma(const float* X, const float* Wf, const int32_t* nbr, const int32_t* order, int64_t n_q, int K,
+                      int mirror, float* Y, cudaStream_t s) {
   constexpr int R = kMmWarps * 16 * MT;
   constexpr size_t smem = (size_t)kMmMaxK * R * 4 + (WS == 0 ? 2 * (size_t)(CIN / 8) * (COUT / 8) * 32 * 16 : 0);
   static bool attr_set = false;
@@ -344,20 +353,20 @@ static int launch_mma(const float* X, const float* Wf, const int32_t* nbr, int64
     attr_set = true;
   }
   const unsigned gx = (unsigned)((n_q + R - 1) / R);
-  conv_mma_kernel<CIN, COUT, MT, WS><<<gx, kMmThreads, smem, s>>>(X, (const float4*)Wf, nbr, n_q, K, mirror, Y);
+  conv_mma_kernel<CIN, COUT, MT, WS><<<gx, kMmThreads, smem, s>>>(X, (const float4*)Wf, nbr, n_q, K, mirror, order, Y);
   return PGS_OK;
 }
 
 template <int CIN, int COUT>
-static int launch_mma_shape(const float* X, const float* Wf, const int32_t* nbr, int64_t n_q, int K, int mirror,
-                            float* Y, int ws, int mt, cudaStream_t s) {
+static int launch_mma_shape(const float* X, const float* Wf, const int32_t* nbr, const int32_t* order, int64_t n_q,
+                            int K, int mirror, float* Y, int ws, int mt, cudaStream_t s) {
   constexpr bool kTwo = (CIN <= 32 && COUT <= 32);   // two m-tiles per warp fit the register file
   if (kTwo && mt != 1) {
-    if (ws) return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 1>(X, Wf, nbr, n_q, K, mirror, Y, s);
-    return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 0>(X, Wf, nbr, n_q, K, mirror, Y, s);
+    if (ws) return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 1>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
+    return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 0>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
   }
-  if (ws) return launch_mma<CIN, COUT, 1, 1>(X, Wf, nbr, n_q, K, mirror, Y, s);
-  return launch_mma<CIN, COUT, 1, 0>(X, Wf, nbr, n_q, K, mirror, Y, s);
+  if (ws) return launch_mma<CIN, COUT, 1, 1>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
+  return launch_mma<CIN, COUT, 1, 0>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
 }
 
 }  // namespace pgs
@@ -374,7 +383,8 @@ size_t pgs_conv_mma_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out) {
   return align_up((size_t)K * c_in * c_out * 2 * sizeof(float), 256);
 }
 
-int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, int64_t n_q, int32_t K, int32_t c_in,
+int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q, int32_t K,
+                     int32_t c_in,
                      int32_t c_out, int32_t mirror, int32_t w_transposed, float* Y, void* scratch,
                      size_t scratch_bytes, void* stream) {
   PGS_CHECK_ARG(K >= 1 && K <= kMmMaxK, "kernel volume must be in 1..27 for the mma path");
@@ -398,7 +408,7 @@ int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, int64_t
   int rc = PGS_ERR_INVALID;
 #define PGS_MMA_CASE(CI, CO)                                                                   \
   case CI * 1000 + CO:                                                                         \
-    rc = launch_mma_shape<CI, CO>(X, Wf, nbr, n_q, K, mirror, Y, ws, mt, s);                   \
+    rc = launch_mma_shape<CI, CO>(X, Wf, nbr, order, n_q, K, mirror, Y, ws, mt, s);                   \
     break;
   switch (c_in * 1000 + c_out) {
     PGS_MMA_CASE(16, 16) PGS_MMA_CASE(16, 32) PGS_MMA_CASE(16, 48) PGS_MMA_CASE(16, 64)
@@ -422,7 +432,8 @@ int pgs_conv_mma_split_supported(int32_t c_in, int32_t c_out) {
 }
 
 /* few-row variant: warp items (16 rows x 16 output channels x part of the offsets), see conv_mma_split_kernel */
-int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, int64_t n_q, int32_t K, int32_t c_in,
+int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q,
+                           int32_t K, int32_t c_in,
                            int32_t c_out, int32_t mirror, int32_t w_transposed, float* Y, void* scratch,
                            size_t scratch_bytes, void* stream) {
   PGS_CHECK_ARG(K >= 1 && K <= kMmMaxK, "kernel volume must be in 1..27 for the mma path");
@@ -452,7 +463,7 @@ int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, i
   const int64_t items = base * ksplit;
   const unsigned gx = (unsigned)((items + kSplitWarps - 1) / kSplitWarps);
   conv_mma_split_kernel<<<gx, kSplitWarps * 32, 0, s>>>(X, (const float4*)Wf, nbr, n_q, K, c_in, c_out, mirror, ksplit,
-                                                        mtiles, Y);
+                                                        mtiles, order, Y);
   count_launch(2);
   PGS_CHECK_LAUNCH();
   return PGS_OK;

@@ -165,7 +165,8 @@ template <int NB>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
                                                               const int32_t* __restrict__ nbr, int64_t n_q, int K,
                                                               int c_in, int c_out, int mirror, uint32_t tmem_cols,
-                                                              int ksplit, float* __restrict__ Y) {
+                                                              int ksplit, const int32_t* __restrict__ order,
+                                                              float* __restrict__ Y) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_empty[kTcStages];
   __shared__ uint64_t bar_done;
@@ -314,7 +315,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
   // epilogue: warp w reads TMEM lanes 32*(w%4).., columns of half (w/4); main + correction tiles summed in fp32
   {
     const int lq = warp & 3, half = warp >> 2;
-    const int64_t r = row0 + lq * 32 + lane;
+    const int64_t rt = row0 + lq * 32 + lane;   // row of the (possibly occupancy-sorted) table
+    const bool r_ok = rt < n_q;
+    const int64_t r = (r_ok && order) ? (int64_t)__ldg(&order[rt]) : rt;   // output row
     const int c_begin = half * (N / 2), c_end = c_begin + N / 2;   // N is a multiple of 16
     for (int c = c_begin; c < c_end; c += 8) {
       uint32_t v[8], u[8];
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0u;
       }
-      if (r < n_q) {
+      if (r_ok) {
         if (ksplit == 1) {
           float4* y = (float4*)(Y + (size_t)r * c_out + c);
           y[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -392,7 +395,9 @@ template <int NBH, int PF>
 __global__ void __launch_bounds__(kTsThreads) conv_ts_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
                                                               const int32_t* __restrict__ nbr, int64_t n_q, int K,
                                                               int c_in, int c_out, int mirror, uint32_t tmem_cols,
-                                                              uint32_t col_a0, int ring, float* __restrict__ Y) {
+                                                              uint32_t col_a0, int ring,
+                                                              const int32_t* __restrict__ order,
+                                                              float* __restrict__ Y) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_empty[kTsMaxRing];
   __shared__ uint64_t bar_done;
@@ -594,7 +599,9 @@ __global__ void __launch_bounds__(kTsThreads) conv_ts_kernel(const float* __rest
     }
     // epilogue: warp w reads TMEM lanes 32*(w%4).., columns of half (w/4); main + correction tiles summed in fp32
     const int lq = warp & 3, half = warp >> 2;
-    const int64_t rr = row0 + lq * 32 + lane;
+    const int64_t rt = row0 + lq * 32 + lane;
+    const bool rr_ok = rt < n_q;
+    const int64_t rr = (rr_ok && order) ? (int64_t)__ldg(&order[rt]) : rt;
     const int c_begin = half * (N / 2), c_end = c_begin + N / 2;   // N is a multiple of 16
     for (int c = c_begin; c < c_end; c += 8) {
       uint32_t v[8], u[8];
@@ -608,7 +615,7 @@ __global__ void __launch_bounds__(kTsThreads) conv_ts_kernel(const float* __rest
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0u;
       }
-      if (rr < n_q) {
+      if (rr_ok) {
         float4* y = (float4*)(Y + (size_t)rr * c_out + c);
         y[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
         y[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
@@ -640,7 +647,8 @@ size_t pgs_conv_tc_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out) {
   return align_up((size_t)K * c_in * c_out * sizeof(float), 256);
 }
 
-int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t n_q, int32_t K, int32_t c_in,
+int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q, int32_t K,
+                    int32_t c_in,
                     int32_t c_out, int32_t mirror, int32_t w_transposed, float* Y, void* scratch,
                     size_t scratch_bytes, void* stream) {
   PGS_CHECK_ARG(K >= 1 && K <= kTcMaxK, "kernel volume must be in 1..27 for the tcgen05 path");
@@ -682,13 +690,13 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t 
     while (ring > 2 && (size_t)ring * 4 * c_out * 64 > 160 * 1024) --ring;
     const size_t sm = (size_t)ring * 4 * c_out * 64;
     if (c_out <= 32)
-      conv_ts_kernel<1, 4><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, Y);
+      conv_ts_kernel<1, 4><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
     else if (c_out <= 64)
-      conv_ts_kernel<2, 3><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, Y);
+      conv_ts_kernel<2, 3><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
     else if (c_out <= 128)
-      conv_ts_kernel<4, 2><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, Y);
+      conv_ts_kernel<4, 2><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
     else
-      conv_ts_kernel<6, 2><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, Y);
+      conv_ts_kernel<6, 2><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
   } else {
     const uint32_t cols = tmem_cols_for(2 * c_out);
     // few row tiles: spread the kernel offsets of a tile over several CTAs (partial tiles meet in Y by atomicAdd)
@@ -700,11 +708,11 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, int64_t 
     if (ksplit > 1) PGS_CUDA(cudaMemsetAsync(Y, 0, (size_t)n_q * c_out * sizeof(float), s));
     const dim3 grid(gx, ksplit);
     if (c_out <= 64)
-      conv_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, Y);
+      conv_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
     else if (c_out <= 128)
-      conv_tc_kernel<2><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, Y);
+      conv_tc_kernel<2><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
     else
-      conv_tc_kernel<3><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, Y);
+      conv_tc_kernel<3><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
   }
   count_launch(2);
   PGS_CHECK_LAUNCH();

@@ -40,13 +40,31 @@ class CoordinateMap:
 
 
 class KernelMap:
-    """Gather table nbr[K, n_q] (+ lazily the ME-style pair lists used by the weight gradient)."""
+    """Gather table nbr[K, n_q] (+ lazily the ME-style pair lists used by the weight gradient and the
+    occupancy-sorted copy used by the tensor-core kernels)."""
 
-    __slots__ = ("nbr", "K", "n_q", "_pairs")
+    __slots__ = ("nbr", "K", "n_q", "_pairs", "_sorted")
 
     def __init__(self, nbr, K, n_q):
         self.nbr, self.K, self.n_q = nbr, K, n_q
         self._pairs = None
+        self._sorted = None
+
+    def sorted(self):
+        """-> (nbr_sorted int32[K, n_q], order int32[n_q]): the table with its rows sorted by their K-bit
+        neighbour-occupancy mask, so that the rows of a 16 / 128-row tile share their empty kernel offsets and the
+        tensor-core kernels skip them (include/pgs_b200.h, pgs_kmap_row_masks).  Tile row r is output row order[r]."""
+        if self._sorted is None:
+            lib = _lib.load()
+            dev = self.nbr.device
+            counts = torch.empty(self.K, dtype=torch.int32, device=dev)
+            masks = torch.empty(max(self.n_q, 1), dtype=torch.int64, device=dev)
+            check(lib.pgs_kmap_row_masks(ptr(self.nbr), self.n_q, self.K, ptr(counts), ptr(masks), stream_ptr()))
+            order = torch.sort(masks[:self.n_q], stable=True)[1].to(torch.int32)
+            nbr_sorted = torch.empty_like(self.nbr)
+            check(lib.pgs_kmap_permute(ptr(self.nbr), self.n_q, self.K, ptr(order), ptr(nbr_sorted), stream_ptr()))
+            self._sorted = (nbr_sorted, order)
+        return self._sorted
 
     def pairs(self):
         """(in_idx, out_idx, offs_dev, max_pairs): rulebook grouped by offset, ascending out row."""
@@ -266,7 +284,7 @@ def cat(*tensors):
 # "tc" / "mma": prefer that tensor-core kernel wherever it supports the shape;  "ffma": always the FFMA kernel.
 # All are CUDA kernels behind the same C ABI.
 import os as _os
-CONV_IMPL = _os.environ.get("PGS_CONV_IMPL", "tc")
+CONV_IMPL = _os.environ.get("PGS_CONV_IMPL", "auto")
 SMALL_COUT = int(_os.environ.get("PGS_SMALL_COUT", "0"))  # measured: the tensor-core path wins even at 16 channels
 
 # bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, flops) per conv launch
@@ -303,13 +321,23 @@ def _conv_kernel_choice(lib, K, c_in, c_out, n_q, has_table):
     return "ffma"
 
 
-def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
-    """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed)."""
+# tensor-core kernels read the occupancy-sorted copy of the gather table (KernelMap.sorted) when there is enough work
+# to pay for sorting it once per kernel map
+SORT_TABLES = _os.environ.get("PGS_SORT_TABLES", "1") == "1"
+SORT_MIN_ROWS = int(_os.environ.get("PGS_SORT_MIN_ROWS", "512"))
+
+
+def _conv_fwd_raw(X, W3, km, n_q, mirror, w_transposed):
+    """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed); km: KernelMap, raw table or None."""
     lib = _lib.load()
     K = W3.shape[0]
     c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
+    nbr = km.nbr if isinstance(km, KernelMap) else km
+    order = None
     Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
     kind = _conv_kernel_choice(lib, K, c_in, c_out, n_q, nbr is not None)
+    if kind != "ffma" and SORT_TABLES and isinstance(km, KernelMap) and n_q >= SORT_MIN_ROWS:
+        nbr, order = km.sorted()
     if kind == "tc":
         nb = lib.pgs_conv_tc_scratch_bytes(K, c_in, c_out)
         scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
@@ -320,13 +348,13 @@ def _conv_fwd_raw(X, W3, nbr, n_q, mirror, w_transposed):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     if kind == "tc":
-        check(lib.pgs_conv_fwd_tc(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
+        check(lib.pgs_conv_fwd_tc(ptr(X), ptr(W3), ptr(nbr), ptr(order), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
                                   ptr(Y), ptr(scratch), nb, stream_ptr()))
     elif kind == "mma":
-        check(lib.pgs_conv_fwd_mma(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
+        check(lib.pgs_conv_fwd_mma(ptr(X), ptr(W3), ptr(nbr), ptr(order), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
                                    ptr(Y), ptr(scratch), nb, stream_ptr()))
     elif kind == "split":
-        check(lib.pgs_conv_fwd_mma_split(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror),
+        check(lib.pgs_conv_fwd_mma_split(ptr(X), ptr(W3), ptr(nbr), ptr(order), n_q, K, c_in, c_out, int(mirror),
                                          int(w_transposed), ptr(Y), ptr(scratch), nb, stream_ptr()))
     else:
         check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
@@ -373,8 +401,7 @@ class _SparseConvFn(torch.autograd.Function):
     def forward(ctx, X, W, km_f, km_b, mirror_f, mirror_b, n_out):
         X = X.contiguous()
         W3 = W.reshape(-1, W.shape[-2], W.shape[-1]).contiguous()
-        nbr = km_f.nbr if km_f is not None else None
-        Y = _conv_fwd_raw(X, W3, nbr, n_out, mirror_f, False)
+        Y = _conv_fwd_raw(X, W3, km_f, n_out, mirror_f, False)
         ctx.save_for_backward(X, W)
         ctx.km_f, ctx.km_b, ctx.mirror_f, ctx.mirror_b = km_f, km_b, mirror_f, mirror_b
         ctx.param = W if isinstance(W, nn.Parameter) else None
@@ -389,8 +416,7 @@ class _SparseConvFn(torch.autograd.Function):
         lib = _lib.load()
         dX = dW = None
         if ctx.needs_input_grad[0]:
-            nbr_b = ctx.km_b.nbr if ctx.km_b is not None else None
-            dX = _conv_fwd_raw(dY, W3, nbr_b, X.shape[0], ctx.mirror_b, True)
+            dX = _conv_fwd_raw(dY, W3, ctx.km_b, X.shape[0], ctx.mirror_b, True)
         if ctx.needs_input_grad[1]:
             direct = (DW_DIRECT and ctx.param is not None and ctx.param.grad is not None
                       and ctx.param.grad.is_contiguous() and ctx.param.grad.dtype == torch.float32

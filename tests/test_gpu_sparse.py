@@ -133,6 +133,77 @@ def test_conv_fwd_bwd_parity(cuda_device, cin, cout, mode):
     assert np.allclose(conv.kernel.grad.cpu().numpy(), dWr, atol=TOL * 10, rtol=TOL)  # sums over ~1e4 pairs
 
 
+@pytest.mark.parametrize("impl", ["tc", "mma", "split", "auto"])
+@pytest.mark.parametrize("sort", [False, True])
+@pytest.mark.parametrize("cin,cout,mode", [(16, 16, "s1"), (32, 48, "s2T"), (64, 64, "s1T"), (64, 16, "s2"),
+                                           (96, 112, "s1"), (16, 32, "s2T")])
+def test_conv_kernel_variants_parity(cuda_device, monkeypatch, impl, sort, cin, cout, mode):
+    """Every tensor-core conv kernel (tcgen05, register-operand mma, few-row split), with and without the
+    occupancy-sorted gather table, against the fp64 oracle: forward, input gradient, weight gradient."""
+    me = _me()
+    monkeypatch.setattr(me, "CONV_IMPL", impl)
+    monkeypatch.setattr(me, "SORT_TABLES", sort)
+    monkeypatch.setattr(me, "SORT_MIN_ROWS", 0)
+    monkeypatch.setattr(me, "MMA_MIN_ROWS", 4000)
+    rng = np.random.default_rng(cin * 1000 + cout)
+    coords = _scene(7, n=9000)
+    ts_in = 2 if mode == "s2T" else 1
+    maps = sr.Maps(coords)
+    mgr = me.CoordinateManager(torch.from_numpy(coords).to(cuda_device))
+    if ts_in == 2:
+        maps.stride(1, 2); mgr.stride(1, 2)
+    n_in = len(maps.coords[ts_in])
+    X = rng.standard_normal((n_in, cin)).astype(np.float32)
+    W = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    stride = 2 if mode in ("s2", "s2T") else 1
+    transpose = mode.endswith("T")
+    nbr_f, mir_f, nbr_b, mir_b, ts_out = maps.conv_maps(ts_in, 3, stride, transpose)
+    Yr = sr.conv_fwd(X, W, nbr_f, mirror=mir_f)
+    dY = rng.standard_normal(Yr.shape).astype(np.float32)
+    dXr, dWr = sr.conv_bwd(X, W, dY, nbr_f, mirror=mir_f)
+    cls = me.MinkowskiConvolutionTranspose if transpose else me.MinkowskiConvolution
+    conv = cls(cin, cout, kernel_size=3, stride=stride, dimension=3).to(cuda_device)
+    with torch.no_grad():
+        conv.kernel.copy_(torch.from_numpy(W))
+    Xt = torch.from_numpy(X).to(cuda_device).requires_grad_(True)
+    out = conv(me.SparseTensor(Xt, coordinate_manager=mgr, tensor_stride=ts_in))
+    out.F.backward(torch.from_numpy(dY).to(cuda_device))
+    assert np.allclose(out.F.detach().cpu().numpy(), Yr, atol=TOL, rtol=TOL)
+    assert np.allclose(Xt.grad.cpu().numpy(), dXr, atol=TOL, rtol=TOL)
+    assert np.allclose(conv.kernel.grad.cpu().numpy(), dWr, atol=TOL * 10, rtol=TOL)
+
+
+def test_sorted_table_is_a_row_permutation_and_changes_nothing(cuda_device, monkeypatch):
+    """KernelMap.sorted(): nbr_sorted[:, r] == nbr[:, order[r]], order is a permutation, the masks are grouped;
+    the mma kernel (no atomics) returns bit-identical rows with and without the sorted table."""
+    me = _me()
+    coords = _scene(11, n=12000)
+    mgr = me.CoordinateManager(torch.from_numpy(coords).to(cuda_device))
+    mgr.stride(1, 2)
+    for km in (mgr.kernel_map(1, 1, 1, 1, 3), mgr.kernel_map(1, 2, 1, -1, 3), mgr.kernel_map(2, 1, 1, 1, 3)):
+        ns, order = km.sorted()
+        o = order.long()
+        assert torch.equal(torch.sort(o)[0], torch.arange(km.n_q, device=cuda_device))
+        assert torch.equal(ns, km.nbr[:, o])
+        occ = (ns >= 0)
+        # rows with identical occupancy are contiguous: the number of mask changes along the sorted rows equals the
+        # number of distinct masks - 1
+        changes = int((occ[:, 1:] != occ[:, :-1]).any(0).sum())
+        distinct = int(torch.unique(occ.t().contiguous(), dim=0).shape[0])
+        assert changes == distinct - 1
+    km = mgr.kernel_map(1, 1, 1, 1, 3)
+    rng = np.random.default_rng(3)
+    X = torch.from_numpy(rng.standard_normal((km.n_q, 32)).astype(np.float32)).to(cuda_device)
+    W = torch.from_numpy((rng.standard_normal((27, 32, 16)) / 30).astype(np.float32)).to(cuda_device)
+    monkeypatch.setattr(me, "CONV_IMPL", "mma")
+    monkeypatch.setattr(me, "SORT_MIN_ROWS", 0)
+    monkeypatch.setattr(me, "SORT_TABLES", False)
+    Y0 = me._conv_fwd_raw(X, W, km, km.n_q, 0, 0)
+    monkeypatch.setattr(me, "SORT_TABLES", True)
+    Y1 = me._conv_fwd_raw(X, W, km, km.n_q, 0, 0)
+    assert torch.equal(Y0, Y1)
+
+
 def test_conv_k1_parity(cuda_device):
     me = _me()
     rng = np.random.default_rng(5)
