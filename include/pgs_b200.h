@@ -246,6 +246,26 @@ int pgs_bn_backward(const float* X, const float* Y, const float* dY, int64_t n, 
                     const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, double* sums,
                     float* dX, float* dweight, float* dbias, void* stream);
 
+/* flags of the _ex variants (used by the fused U-Net executor, fastpath.py) */
+#define PGS_BN_ACCUMULATE_PARAM_GRADS 1 /* dweight / dbias += instead of = (write straight into param.grad) */
+#define PGS_BN_SUMS_ZEROED 2            /* the caller zeroed `sums` (one memset for all layers of a pass) */
+int pgs_bn_forward_ex(const float* X, int64_t n, int32_t C, const float* weight, const float* bias,
+                      float* running_mean, float* running_var, int32_t training, float momentum, float eps,
+                      int32_t relu, int32_t flags, double* sums, float* save_mean, float* save_invstd, float* Y,
+                      void* stream);
+int pgs_bn_backward_ex(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
+                       const float* save_mean, const float* save_invstd, int32_t training, int32_t relu,
+                       int32_t flags, double* sums, float* dX, float* dweight, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Feature-matrix glue of the U-Net (replaces `a + b` and ME.cat on SparseTensors sharing a coordinate map;
+ * reference: api_modules.py:76-82 (residual sum), 306-311 (skip concatenation)).
+ *   pgs_add2 : y = a + b over n_elems floats (multiple of 4)
+ *   pgs_cat2 : split == 0: y[r] = [a[r] | b[r]]   split == 1: a[r], b[r] = the two parts of y[r]  (backward of cat)
+ * ------------------------------------------------------------------------------------------ */
+int pgs_add2(const float* a, const float* b, float* y, int64_t n_elems, void* stream);
+int pgs_cat2(float* a, int32_t ca, float* b, int32_t cb, float* y, int64_t n, int32_t split, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,12 @@ SIGNATURES = {
                                c_float, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_bn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                 c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgs_bn_forward_ex": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
+                                  c_float, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgs_bn_backward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                   c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgs_add2": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "pgs_cat2": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
     "pgs_conv_bwd_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     c_int32, c_int32, c_int32, c_void_p, c_void_p]),
 }

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import me as ME
+from . import fastpath
 
 
 class ResBlock(ME.MinkowskiNetwork):
@@ -219,6 +220,9 @@ class Output:
 class MinkowskiUnet(BaseMinkowski):
     def forward(self, data, *args, **kwargs):
         self._set_input(data)
+        x = fastpath.run(self, self.input)   # whole backbone as one autograd node (same kernels, no per-layer host cost)
+        if x is not None:
+            return Output(x=x.F, pos=self.xyz, batch=x.C[:, 0])
         x = self.input
         stack_down = []
         for i in range(len(self.down_modules) - 1):
@@ -234,9 +238,11 @@ class MinkowskiUnet(BaseMinkowski):
 class MinkowskiEncoder(BaseMinkowski):
     def forward(self, data, *args, **kwargs):
         self._set_input(data)
-        x = self.input
-        for m in self.down_modules:
-            x = m(x)
+        x = fastpath.run(self, self.input)
+        if x is None:
+            x = self.input
+            for m in self.down_modules:
+                x = m(x)
         return Output(x=x.F, batch=x.C[:, 0].long())
 
 

@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_stats_kernel(
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ dY, int64_t n, int C,
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, const float* __restrict__ weight,
-    const double* __restrict__ sums, int training, int relu, float* __restrict__ dX, float* __restrict__ dweight,
-    float* __restrict__ dbias) {
+    const double* __restrict__ sums, int training, int relu, int accumulate, float* __restrict__ dX,
+    float* __restrict__ dweight, float* __restrict__ dbias) {
   extern __shared__ float bn_sm[];   // [4][C]: mean, invstd * w, mean_g, mean_gh * invstd... see below
   float* a_mean = bn_sm;
   float* a_inv = bn_sm + C;
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     a_mg[c] = training ? (float)(sums[c] / (double)n) : 0.f;
     a_mgh[c] = training ? (float)(sums[C + c] / (double)n) : 0.f;
     if (blockIdx.x == 0) {
-      if (dbias) dbias[c] = (float)sums[c];
-      if (dweight) dweight[c] = (float)sums[C + c];
+      if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)sums[c];
+      if (dweight) dweight[c] = (accumulate ? dweight[c] : 0.f) + (float)sums[C + c];
     }
   }
   __syncthreads();
@@ -184,6 +184,34 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// feature-matrix glue of the U-Net: residual add, channel concatenation and its split (ME.cat / "+" on SparseTensors,
+// api_modules.py:76-82,306-311) -- float4 grid-stride kernels, rows are multiples of 4 channels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add2_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                   float4* __restrict__ y, int64_t n4) {
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n4; e += (int64_t)gridDim.x * 256) {
+    const float4 u = __ldg(a + e), v = __ldg(b + e);
+    y[e] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+// y[r] = [a[r] | b[r]]  (split = 0)   or   a[r], b[r] = halves of y[r]  (split = 1)
+__global__ void __launch_bounds__(256) cat2_kernel(float4* __restrict__ a, int ca4, float4* __restrict__ b, int cb4,
+                                                   float4* __restrict__ y, int64_t n, int split) {
+  const int c4 = ca4 + cb4;
+  const int64_t total = n * c4;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int64_t r = e / c4;
+    const int c = (int)(e - r * c4);
+    float4* src = (c < ca4) ? (a + r * ca4 + c) : (b + r * cb4 + (c - ca4));
+    if (split)
+      *src = y[e];
+    else
+      y[e] = *src;
+  }
+}
+
 static inline int bn_apply_grid(int64_t total4) {
   int64_t g = (total4 + kBnThreads - 1) / kBnThreads;
   const int64_t cap = (int64_t)kNumSM * 8;
@@ -199,12 +227,19 @@ extern "C" {
 int pgs_bn_forward(const float* X, int64_t n, int32_t C, const float* weight, const float* bias, float* running_mean,
                    float* running_var, int32_t training, float momentum, float eps, int32_t relu, double* sums,
                    float* save_mean, float* save_invstd, float* Y, void* stream) {
+  return pgs_bn_forward_ex(X, n, C, weight, bias, running_mean, running_var, training, momentum, eps, relu, 0, sums,
+                           save_mean, save_invstd, Y, stream);
+}
+
+int pgs_bn_forward_ex(const float* X, int64_t n, int32_t C, const float* weight, const float* bias, float* running_mean,
+                      float* running_var, int32_t training, float momentum, float eps, int32_t relu, int32_t flags,
+                      double* sums, float* save_mean, float* save_invstd, float* Y, void* stream) {
   PGS_CHECK_ARG(C >= 4 && C % 4 == 0 && C <= 1024, "channel count must be a multiple of 4, at most 1024");
   PGS_CHECK_ARG(training || (running_mean && running_var), "eval mode needs running statistics");
   if (n == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (training) {
-    PGS_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
+    if (!(flags & PGS_BN_SUMS_ZEROED)) PGS_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
     const unsigned g = (unsigned)((n + kBnRowsPerBlock - 1) / kBnRowsPerBlock);
     const dim3 blk(C / 4, kBnThreads / (C / 4));
     bn_stats_kernel<<<g, blk, (size_t)blk.y * 2 * C * sizeof(float), s>>>(X, n, C, sums);
@@ -220,18 +255,46 @@ int pgs_bn_forward(const float* X, int64_t n, int32_t C, const float* weight, co
 int pgs_bn_backward(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
                     const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, double* sums,
                     float* dX, float* dweight, float* dbias, void* stream) {
+  return pgs_bn_backward_ex(X, Y, dY, n, C, weight, save_mean, save_invstd, training, relu, 0, sums, dX, dweight, dbias,
+                            stream);
+}
+
+int pgs_bn_backward_ex(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
+                       const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, int32_t flags,
+                       double* sums, float* dX, float* dweight, float* dbias, void* stream) {
   PGS_CHECK_ARG(C >= 4 && C % 4 == 0 && C <= 1024, "channel count must be a multiple of 4, at most 1024");
   PGS_CHECK_ARG(!relu || Y != nullptr, "the ReLU mask needs the forward output");
   if (n == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  PGS_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
+  if (!(flags & PGS_BN_SUMS_ZEROED)) PGS_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
   const unsigned g = (unsigned)((n + kBnRowsPerBlock - 1) / kBnRowsPerBlock);
   const dim3 blk(C / 4, kBnThreads / (C / 4));
   bn_bwd_stats_kernel<<<g, blk, (size_t)blk.y * 2 * C * sizeof(float), s>>>(X, Y, dY, n, C, save_mean, save_invstd, relu,
                                                                           sums);
   bn_bwd_apply_kernel<<<bn_apply_grid(n * (C / 4)), kBnThreads, 5 * C * sizeof(float), s>>>(
-      X, Y, dY, n, C, save_mean, save_invstd, weight, sums, training, relu, dX, dweight, dbias);
+      X, Y, dY, n, C, save_mean, save_invstd, weight, sums, training, relu, (flags & PGS_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0,
+      dX, dweight, dbias);
   count_launch(2);
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+int pgs_add2(const float* a, const float* b, float* y, int64_t n_elems, void* stream) {
+  PGS_CHECK_ARG(n_elems % 4 == 0, "element count must be a multiple of 4");
+  if (n_elems == 0) return PGS_OK;
+  add2_kernel<<<bn_apply_grid(n_elems / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, (float4*)y,
+                                                                            n_elems / 4);
+  count_launch();
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+int pgs_cat2(float* a, int32_t ca, float* b, int32_t cb, float* y, int64_t n, int32_t split, void* stream) {
+  PGS_CHECK_ARG(ca % 4 == 0 && cb % 4 == 0 && ca > 0 && cb > 0, "channel counts must be positive multiples of 4");
+  if (n == 0) return PGS_OK;
+  cat2_kernel<<<bn_apply_grid(n * ((ca + cb) / 4)), 256, 0, (cudaStream_t)stream>>>((float4*)a, ca / 4, (float4*)b, cb / 4,
+                                                                                   (float4*)y, n, split);
+  count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;
 }

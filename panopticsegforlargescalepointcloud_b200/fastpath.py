@@ -1,0 +1,380 @@
+"""Fused executor for the sparse ResUNet: the whole backbone as ONE autograd node.
+
+Why: the module-by-module mirror of the reference (`backbone.py` on top of `me.py`, same classes and call order as
+torch_points3d/modules/MinkowskiEngine/api_modules.py:9-82,235-311 and applications/minkowski.py:160-196) costs
+~50 us of Python / autograd bookkeeping per layer call: 82 convolutions + 82 batch norms + ReLUs, sums and
+concatenations, forward and backward, add up to ~25 ms of host time per step -- more than the B200 needs for the
+kernels (profiles/r1_host_profile.txt).  The network structure is static, so it is compiled once into a flat tape
+(conv / bn(+relu) / add / cat over numbered feature slots); a step then is
+
+    forward : one pass over the tape, one C-ABI call per op, activations in one arena allocation
+    backward: the tape in reverse -- input gradient = the same conv kernel on the sibling table with W^T, weight
+              gradient accumulated straight into `param.grad` (when it exists), fused BN(+ReLU) backward, gradients
+              of multiply-used tensors (residual inputs, skip connections) merged with one add kernel
+
+The kernels, their dispatch (`me._conv_launch`) and therefore the results are the ones of the module path; the
+module path stays as the reference implementation of this file (tests/test_gpu_fastpath.py compares outputs,
+input / parameter gradients and BN running statistics) and is used whenever the module tree is not the plain
+ResNetDown / ResNetUp / ResBlock structure (`Unsupported`).  PGS_FASTPATH=0 disables it.
+"""
+import os
+
+import torch
+
+from . import _lib
+from . import me as ME
+from ._lib import check
+
+ENABLED = os.environ.get("PGS_FASTPATH", "1") == "1"
+
+OP_CONV, OP_BN, OP_ADD, OP_CAT = 0, 1, 2, 3
+BN_ACC, BN_ZEROED = 1, 2   # include/pgs_b200.h: PGS_BN_ACCUMULATE_PARAM_GRADS, PGS_BN_SUMS_ZEROED
+
+
+class Unsupported(Exception):
+    pass
+
+
+class Program:
+    """Static tape of a MinkowskiUnet / MinkowskiEncoder (built once per model)."""
+
+    def __init__(self, net):
+        from . import backbone as B
+        self._B = B
+        self.ops = []       # (kind, a, b, dst, index into convs / bns, relu)
+        self.convs = []
+        self.bns = []
+        self.n_slots = 1    # slot 0 = network input
+        x = 0
+        if isinstance(net, B.MinkowskiUnet):
+            stack = []
+            for i in range(len(net.down_modules) - 1):
+                x = self._resnet(net.down_modules[i], x)
+                stack.append(x)
+            x = self._resnet(net.down_modules[-1], x)
+            stack.append(None)
+            for m in net.up_modules:
+                skip = stack.pop()
+                if skip is not None:
+                    x = self._emit(OP_CAT, x, skip)
+                x = self._resnet(m, x)
+        elif isinstance(net, B.MinkowskiEncoder):
+            for m in net.down_modules:
+                x = self._resnet(m, x)
+        else:
+            raise Unsupported("not a MinkowskiUnet / MinkowskiEncoder")
+        self.out_slot = x
+        self.params = ([c.kernel for c in self.convs] + [b.bn.weight for b in self.bns] + [b.bn.bias for b in self.bns])
+        self.consumers = [0] * self.n_slots
+        for kind, a, b, dst, idx, relu in self.ops:
+            self.consumers[a] += 1
+            if b >= 0:
+                self.consumers[b] += 1
+        self.scratch = None
+
+    def out_tensor_stride(self, ts0):
+        ts = {0: ts0}
+        for kind, a, b, dst, idx, relu in self.ops:
+            t = ts[a]
+            if kind == OP_CONV:
+                mod = self.convs[idx]
+                t = t // mod.stride if mod.TRANSPOSE else t * mod.stride
+            ts[dst] = t
+        return ts[self.out_slot]
+
+    # ---- tape construction -------------------------------------------------------------------
+    def _emit(self, kind, a, b=-1, idx=-1, relu=False):
+        dst = self.n_slots
+        self.n_slots += 1
+        self.ops.append((kind, a, b, dst, idx, relu))
+        return dst
+
+    def _conv(self, mod, src):
+        if type(mod) not in (ME.MinkowskiConvolution, ME.MinkowskiConvolutionTranspose) or mod.bias is not None:
+            raise Unsupported("convolution %r" % (mod,))
+        self.convs.append(mod)
+        return self._emit(OP_CONV, src, idx=len(self.convs) - 1)
+
+    def _bn(self, mod, src, relu):
+        if type(mod) is not ME.MinkowskiBatchNorm:
+            raise Unsupported("normalisation %r" % (mod,))
+        bn = mod.bn
+        if not (bn.affine and bn.track_running_stats and bn.num_features % 4 == 0 and bn.num_features <= 1024):
+            raise Unsupported("batch norm configuration")
+        self.bns.append(mod)
+        return self._emit(OP_BN, src, idx=len(self.bns) - 1, relu=relu)
+
+    def _conv_bn(self, seq, src):
+        mods = list(seq)
+        if len(mods) == 3 and type(mods[2]) is ME.MinkowskiReLU:
+            relu = True
+        elif len(mods) == 2:
+            relu = False
+        else:
+            raise Unsupported("conv block %r" % (seq,))
+        return self._bn(mods[1], self._conv(mods[0], src), relu)
+
+    def _resnet(self, m, src):
+        B = self._B
+        if type(m) not in (B.ResNetDown, B.ResNetUp):
+            raise Unsupported("module %r" % type(m))
+        y = self._conv_bn(m.conv_in, src)
+        for blk in (m.blocks if m.blocks is not None else ()):
+            if type(blk) is not B.ResBlock:
+                raise Unsupported("block %r" % type(blk))
+            mods = list(blk.block)
+            if len(mods) != 6 or type(mods[2]) is not ME.MinkowskiReLU or type(mods[5]) is not ME.MinkowskiReLU:
+                raise Unsupported("residual block layout")
+            a = self._bn(mods[1], self._conv(mods[0], y), True)
+            b = self._bn(mods[4], self._conv(mods[3], a), True)
+            s = y if blk.downsample is None else self._conv_bn(blk.downsample, y)
+            y = self._emit(OP_ADD, b, s)
+        return y
+
+
+def _stream():
+    return _lib.stream_ptr()
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prog, cm, ts0, X, *params):
+        lib = _lib.load()
+        sp = _stream()
+        X = X.contiguous()
+        dev = X.device
+        S = prog.n_slots
+        n, C, ts = [0] * S, [0] * S, [0] * S
+        n[0], C[0], ts[0] = X.shape[0], X.shape[1], ts0
+        # ---- pass 1: shapes, coordinate / kernel maps (the only data-dependent part) ----
+        cinfo = [None] * len(prog.convs)
+        scratch_bytes = 0
+        for kind, a, b, dst, idx, relu in prog.ops:
+            if kind == OP_CONV:
+                mod = prog.convs[idx]
+                if C[a] != mod.in_channels:
+                    raise ValueError("expected %d input channels, got %d" % (mod.in_channels, C[a]))
+                km_f, km_b, mf, mb, ts_out, n_out = mod.maps_for(cm, ts[a], n[a])
+                K = mod.kernel_size ** 3
+                cinfo[idx] = (km_f, km_b, mf, mb, K)
+                n[dst], C[dst], ts[dst] = n_out, mod.out_channels, ts_out
+                scratch_bytes = max(scratch_bytes, ME._conv_scratch_bytes(lib, K, mod.in_channels, mod.out_channels),
+                                    ME._conv_scratch_bytes(lib, K, mod.out_channels, mod.in_channels))
+            elif kind == OP_BN:
+                if prog.bns[idx].bn.momentum is None:
+                    raise Unsupported("cumulative-average batch norm")
+                n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
+            elif kind == OP_ADD:
+                if (n[a], C[a], ts[a]) != (n[b], C[b], ts[b]):
+                    raise ValueError("sum of sparse tensors on different maps")
+                n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
+            else:
+                if (n[a], ts[a]) != (n[b], ts[b]):
+                    raise ValueError("concatenation of sparse tensors on different maps")
+                n[dst], C[dst], ts[dst] = n[a], C[a] + C[b], ts[a]
+        if min(n) <= 0:
+            raise Unsupported("empty level")
+        # ---- arenas ----
+        off = [0] * (S + 1)
+        for s in range(1, S):
+            off[s + 1] = off[s] + n[s] * C[s]
+        arena = torch.empty(off[S], dtype=torch.float32, device=dev)
+        base = arena.data_ptr()
+        ptrs = [base + 4 * o for o in off[:S]]
+        ptrs[0] = X.data_ptr()
+        nbn = len(prog.bns)
+        soff = [0] * (nbn + 1)
+        for i, m in enumerate(prog.bns):
+            soff[i + 1] = soff[i] + 2 * m.bn.num_features
+        stats = torch.empty(soff[nbn], dtype=torch.float32, device=dev)
+        sums = torch.zeros(soff[nbn], dtype=torch.float64, device=dev)
+        stats_p, sums_p = stats.data_ptr(), sums.data_ptr()
+        if prog.scratch is None or prog.scratch.numel() < scratch_bytes or prog.scratch.device != dev:
+            prog.scratch = torch.empty(max(scratch_bytes, 1), dtype=torch.uint8, device=dev)
+        scratch_p, scratch_n = prog.scratch.data_ptr(), prog.scratch.numel()
+        nconv = len(prog.convs)
+        training = [False] * nbn
+        tracked = []
+        # ---- pass 2: launches ----
+        for kind, a, b, dst, idx, relu in prog.ops:
+            if kind == OP_CONV:
+                mod = prog.convs[idx]
+                km_f, km_b, mf, mb, K = cinfo[idx]
+                ME._conv_launch(lib, ptrs[a], n[a], params[idx].data_ptr(), K, mod.in_channels, mod.out_channels, km_f,
+                                n[dst], mf, False, ptrs[dst], scratch_p, scratch_n, sp)
+            elif kind == OP_BN:
+                bn = prog.bns[idx].bn
+                tr = bool(bn.training)
+                training[idx] = tr
+                if tr and bn.num_batches_tracked is not None:
+                    tracked.append(bn.num_batches_tracked)
+                Cb = C[a]
+                rc = lib.pgs_bn_forward_ex(ptrs[a], n[a], Cb, params[nconv + idx].data_ptr(),
+                                           params[nconv + nbn + idx].data_ptr(), bn.running_mean.data_ptr(),
+                                           bn.running_var.data_ptr(), int(tr), float(bn.momentum), float(bn.eps),
+                                           int(relu), BN_ZEROED, sums_p + 8 * soff[idx], stats_p + 4 * soff[idx],
+                                           stats_p + 4 * (soff[idx] + Cb), ptrs[dst], sp)
+                if rc:
+                    check(rc)
+            elif kind == OP_ADD:
+                rc = lib.pgs_add2(ptrs[a], ptrs[b], ptrs[dst], n[a] * C[a], sp)
+                if rc:
+                    check(rc)
+            else:
+                rc = lib.pgs_cat2(ptrs[a], C[a], ptrs[b], C[b], ptrs[dst], n[a], 0, sp)
+                if rc:
+                    check(rc)
+        if tracked:
+            torch._foreach_add_(tracked, 1)
+        o = prog.out_slot
+        out = arena[off[o]:off[o] + n[o] * C[o]].view(n[o], C[o])
+        ctx.prog, ctx.rt = prog, (n, C, ptrs, cinfo, soff, training, arena, stats)
+        ctx.save_for_backward(X, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        lib = _lib.load()
+        sp = _stream()
+        prog = ctx.prog
+        n, C, ptrs, cinfo, soff, training, arena, stats = ctx.rt
+        saved = ctx.saved_tensors
+        X, params = saved[0], saved[1:]
+        dev = X.device
+        dOut = dOut.contiguous()
+        nconv, nbn = len(prog.convs), len(prog.bns)
+        need_x = ctx.needs_input_grad[3]
+        # ---- gradient arena: one buffer per conv / bn input, per cat input, per merge of a multiply-used slot ----
+        total = 0
+        for kind, a, b, dst, idx, relu in prog.ops:
+            if kind in (OP_CONV, OP_BN):
+                total += n[a] * C[a]
+            elif kind == OP_CAT:
+                total += n[a] * (C[a] + C[b])
+        for s in range(prog.n_slots):
+            if prog.consumers[s] > 1:
+                total += (prog.consumers[s] - 1) * n[s] * C[s]
+        garena = torch.empty(total, dtype=torch.float32, device=dev)
+        gbase, gused = garena.data_ptr(), 0
+        sums = torch.zeros(soff[nbn], dtype=torch.float64, device=dev)
+        sums_p, stats_p = sums.data_ptr(), stats.data_ptr()
+        scratch_p, scratch_n = prog.scratch.data_ptr(), prog.scratch.numel()
+        # parameter gradients: straight into param.grad where it exists (accumulate), else into one zeroed buffer
+        P = prog.params
+        needs = ctx.needs_input_grad[4:]
+        direct = [needs[i] and P[i].grad is not None and P[i].grad.is_contiguous() and P[i].grad.dtype == torch.float32
+                  and P[i].grad.device == dev for i in range(len(P))]
+        goff = [0] * (len(P) + 1)
+        for i, p in enumerate(P):
+            goff[i + 1] = goff[i] + (p.numel() if (needs[i] and not direct[i]) else 0)
+        gflat = torch.zeros(goff[-1], dtype=torch.float32, device=dev) if goff[-1] else None
+        gflat_p = gflat.data_ptr() if gflat is not None else 0
+
+        def pgrad(i):
+            if not needs[i]:
+                return None
+            return P[i].grad.data_ptr() if direct[i] else gflat_p + 4 * goff[i]
+
+        glist = [[] for _ in range(prog.n_slots)]
+        glist[prog.out_slot].append(dOut.data_ptr())
+        for kind, a, b, dst, idx, relu in reversed(prog.ops):
+            gl = glist[dst]
+            if not gl:
+                continue
+            g = gl[0]
+            for extra in gl[1:]:   # tensor with several consumers: sum their gradients
+                buf = gbase + 4 * gused
+                gused += n[dst] * C[dst]
+                rc = lib.pgs_add2(g, extra, buf, n[dst] * C[dst], sp)
+                if rc:
+                    check(rc)
+                g = buf
+            if kind == OP_CONV:
+                mod = prog.convs[idx]
+                km_f, km_b, mf, mb, K = cinfo[idx]
+                cin, cout = mod.in_channels, mod.out_channels
+                wp = params[idx].data_ptr()
+                if a != 0 or need_x:
+                    dx = gbase + 4 * gused
+                    gused += n[a] * C[a]
+                    ME._conv_launch(lib, g, n[dst], wp, K, cout, cin, km_b, n[a], mb, True, dx, scratch_p, scratch_n, sp)
+                    glist[a].append(dx)
+                dw = pgrad(idx)
+                if dw is not None:
+                    if km_f is not None:
+                        in_idx, out_idx, offs, max_pairs = km_f.pairs()
+                        rc = lib.pgs_conv_bwd_weight(ptrs[a], g, in_idx.data_ptr(), out_idx.data_ptr(), offs.data_ptr(),
+                                                     max_pairs, K, cin, cout, int(mf), dw, sp)
+                    else:
+                        rc = lib.pgs_conv_bwd_weight(ptrs[a], g, None, None, None, n[a], 1, cin, cout, 0, dw, sp)
+                    if rc:
+                        check(rc)
+            elif kind == OP_BN:
+                Cb = C[a]
+                dx = gbase + 4 * gused
+                gused += n[a] * Cb
+                iw, ib = nconv + idx, nconv + nbn + idx
+                flags = BN_ZEROED | (BN_ACC if (direct[iw] or direct[ib]) else 0)
+                if direct[iw] != direct[ib] and needs[iw] and needs[ib]:
+                    raise RuntimeError("batch-norm weight and bias must both have (or both lack) a .grad buffer")
+                rc = lib.pgs_bn_backward_ex(ptrs[a], ptrs[dst] if relu else None, g, n[a], Cb, params[iw].data_ptr(),
+                                            stats_p + 4 * soff[idx], stats_p + 4 * (soff[idx] + Cb), int(training[idx]),
+                                            int(relu), flags, sums_p + 8 * soff[idx], dx, pgrad(iw), pgrad(ib), sp)
+                if rc:
+                    check(rc)
+                glist[a].append(dx)
+            elif kind == OP_ADD:
+                glist[a].append(g)
+                glist[b].append(g)
+            else:
+                ga = gbase + 4 * gused
+                gused += n[a] * C[a]
+                gb = gbase + 4 * gused
+                gused += n[b] * C[b]
+                rc = lib.pgs_cat2(ga, C[a], gb, C[b], g, n[a], 1, sp)
+                if rc:
+                    check(rc)
+                glist[a].append(ga)
+                glist[b].append(gb)
+        assert gused <= total
+        dX = None
+        if need_x:
+            g0 = glist[0]
+            off0 = (g0[0] - gbase) // 4
+            dX = garena[off0:off0 + n[0] * C[0]].view(n[0], C[0])
+            for extra in g0[1:]:
+                o2 = (extra - gbase) // 4
+                dX = dX + garena[o2:o2 + n[0] * C[0]].view(n[0], C[0])
+        grads = []
+        for i, p in enumerate(P):
+            if not needs[i] or direct[i]:
+                grads.append(None)
+            else:
+                grads.append(gflat[goff[i]:goff[i + 1]].view(p.shape))
+        return (None, None, None, dX) + tuple(grads)
+
+
+def program_for(net):
+    """Compiled tape of `net` (cached on the module), or None when its structure is not supported."""
+    prog = net.__dict__.get("_pgs_program", False)
+    if prog is False:
+        try:
+            prog = Program(net)
+        except Unsupported:
+            prog = None
+        net.__dict__["_pgs_program"] = prog
+    return prog
+
+
+def run(net, x):
+    """Output SparseTensor of the network for the input SparseTensor `x`, or None when the fast path does not apply."""
+    if not ENABLED:
+        return None
+    prog = program_for(net)
+    if prog is None:
+        return None
+    try:
+        F = _UNetFn.apply(prog, x.coordinate_manager, x.tensor_stride, x.F, *prog.params)
+    except Unsupported:
+        return None
+    return ME.SparseTensor(F, coordinate_manager=x.coordinate_manager, tensor_stride=prog.out_tensor_stride(x.tensor_stride))

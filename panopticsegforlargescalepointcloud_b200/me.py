@@ -327,43 +327,64 @@ SORT_TABLES = _os.environ.get("PGS_SORT_TABLES", "1") == "1"
 SORT_MIN_ROWS = int(_os.environ.get("PGS_SORT_MIN_ROWS", "512"))
 
 
-def _conv_fwd_raw(X, W3, km, n_q, mirror, w_transposed):
-    """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed); km: KernelMap, raw table or None."""
-    lib = _lib.load()
-    K = W3.shape[0]
-    c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
-    nbr = km.nbr if isinstance(km, KernelMap) else km
-    order = None
-    Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
-    kind = _conv_kernel_choice(lib, K, c_in, c_out, n_q, nbr is not None)
-    if kind != "ffma" and SORT_TABLES and isinstance(km, KernelMap) and n_q >= SORT_MIN_ROWS:
-        nbr, order = km.sorted()
-    if kind == "tc":
+def _conv_scratch_bytes(lib, K, c_in, c_out):
+    """Scratch that any conv kernel may need for this shape (the re-arranged weights)."""
+    nb = 0
+    if lib.pgs_conv_tc_supported(c_in, c_out):
         nb = lib.pgs_conv_tc_scratch_bytes(K, c_in, c_out)
-        scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
-    elif kind in ("mma", "split"):
-        nb = lib.pgs_conv_mma_scratch_bytes(K, c_in, c_out)
-        scratch = torch.empty(nb, dtype=torch.uint8, device=X.device)
+    if lib.pgs_conv_mma_split_supported(c_in, c_out):
+        nb = max(nb, lib.pgs_conv_mma_scratch_bytes(K, c_in, c_out))
+    return nb
+
+
+def _conv_launch(lib, Xp, n_in, Wp, K, c_in, c_out, km, n_q, mirror, w_transposed, Yp, scratch_p, scratch_bytes, sp):
+    """Pick the kernel for this shape and launch it on raw device pointers (ints); returns the kernel kind.
+    km: KernelMap, raw table tensor or None (K == 1 identity)."""
+    nbr = km.nbr if isinstance(km, KernelMap) else km
+    kind = _conv_kernel_choice(lib, K, c_in, c_out, n_q, nbr is not None)
+    nbr_p = order_p = None
+    if nbr is not None:
+        if kind != "ffma" and SORT_TABLES and isinstance(km, KernelMap) and n_q >= SORT_MIN_ROWS:
+            ns, order = km.sorted()
+            nbr_p, order_p = ns.data_ptr(), order.data_ptr()
+        else:
+            nbr_p = nbr.data_ptr()
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     if kind == "tc":
-        check(lib.pgs_conv_fwd_tc(ptr(X), ptr(W3), ptr(nbr), ptr(order), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
-                                  ptr(Y), ptr(scratch), nb, stream_ptr()))
+        rc = lib.pgs_conv_fwd_tc(Xp, Wp, nbr_p, order_p, n_q, K, c_in, c_out, int(mirror), int(w_transposed), Yp,
+                                 scratch_p, scratch_bytes, sp)
     elif kind == "mma":
-        check(lib.pgs_conv_fwd_mma(ptr(X), ptr(W3), ptr(nbr), ptr(order), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
-                                   ptr(Y), ptr(scratch), nb, stream_ptr()))
+        rc = lib.pgs_conv_fwd_mma(Xp, Wp, nbr_p, order_p, n_q, K, c_in, c_out, int(mirror), int(w_transposed), Yp,
+                                  scratch_p, scratch_bytes, sp)
     elif kind == "split":
-        check(lib.pgs_conv_fwd_mma_split(ptr(X), ptr(W3), ptr(nbr), ptr(order), n_q, K, c_in, c_out, int(mirror),
-                                         int(w_transposed), ptr(Y), ptr(scratch), nb, stream_ptr()))
+        rc = lib.pgs_conv_fwd_mma_split(Xp, Wp, nbr_p, order_p, n_q, K, c_in, c_out, int(mirror), int(w_transposed), Yp,
+                                        scratch_p, scratch_bytes, sp)
     else:
-        check(lib.pgs_conv_fwd(ptr(X), ptr(W3), ptr(nbr), n_q, K, c_in, c_out, int(mirror), int(w_transposed),
-                               ptr(Y), stream_ptr()))
+        rc = lib.pgs_conv_fwd(Xp, Wp, nbr_p, n_q, K, c_in, c_out, int(mirror), int(w_transposed), Yp, sp)
+    if rc != 0:
+        check(rc)
     if PROFILE is not None:
         e1.record()
         pairs = int((nbr >= 0).sum()) if (nbr is not None and PROFILE_COUNT_PAIRS) else (n_q if nbr is None else 0)
-        PROFILE.append((e0, e1, conv_algorithmic_bytes(X.shape[0], n_q, K, c_in, c_out, nbr is not None),
-                        2 * pairs * c_in * c_out, (X.shape[0], n_q, K, c_in, c_out), kind))
+        PROFILE.append((e0, e1, conv_algorithmic_bytes(n_in, n_q, K, c_in, c_out, nbr is not None),
+                        2 * pairs * c_in * c_out, (n_in, n_q, K, c_in, c_out), kind))
+    return kind
+
+
+def _conv_fwd_raw(X, W3, km, n_q, mirror, w_transposed):
+    """Y[q] = sum_k X[nbr[tk(k)][q]] W3[k]  (or with W3[k]^T when w_transposed); km: KernelMap, raw table or None."""
+    lib = _lib.load()
+    if not (X.is_cuda and W3.is_cuda):
+        raise _lib.PgsError("expected CUDA tensors: the B200 path has no CPU implementation")
+    K = W3.shape[0]
+    c_in, c_out = (W3.shape[2], W3.shape[1]) if w_transposed else (W3.shape[1], W3.shape[2])
+    Y = torch.empty((n_q, c_out), dtype=torch.float32, device=X.device)
+    nb = _conv_scratch_bytes(lib, K, c_in, c_out)
+    scratch = torch.empty(max(nb, 1), dtype=torch.uint8, device=X.device)
+    _conv_launch(lib, ptr(X).value, X.shape[0], ptr(W3).value, K, c_in, c_out, km, n_q, mirror, w_transposed,
+                 Y.data_ptr(), scratch.data_ptr(), nb, stream_ptr())
     return Y
 
 
@@ -507,13 +528,15 @@ class MinkowskiConvolutionBase(nn.Module):
                 self.bias.uniform_(-stdv, stdv)
 
     def _maps(self, x: SparseTensor):
-        """-> (km_fwd, km_bwd, mirror_f, mirror_b, out_tensor_stride, n_out)"""
-        cm, ts = x.coordinate_manager, x.tensor_stride
+        return self.maps_for(x.coordinate_manager, x.tensor_stride, x.F.shape[0])
+
+    def maps_for(self, cm, ts, n_in):
+        """-> (km_fwd, km_bwd, mirror_f, mirror_b, out_tensor_stride, n_out) for an input on map `ts` of `cm`"""
         ks = self.kernel_size
         if not self.TRANSPOSE:
             if self.stride == 1:
                 if ks == 1:
-                    return None, None, False, False, ts, x.F.shape[0]
+                    return None, None, False, False, ts, n_in
                 km = cm.kernel_map(ts, ts, ts, +1, ks)
                 return km, km, False, True, ts, km.n_q
             ts_out = ts * self.stride
@@ -524,7 +547,7 @@ class MinkowskiConvolutionBase(nn.Module):
         # transposed
         if self.stride == 1:
             if ks == 1:
-                return None, None, False, False, ts, x.F.shape[0]
+                return None, None, False, False, ts, n_in
             km = cm.kernel_map(ts, ts, ts, +1, ks)
             return km, km, True, False, ts, km.n_q
         if ts % self.stride != 0 or (ts // self.stride) not in cm.maps:

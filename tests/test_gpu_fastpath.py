@@ -1,0 +1,106 @@
+"""Fused U-Net executor (fastpath.py) against the per-layer module path it replaces and against the CPU restatement.
+
+Same model object, same inputs: outputs, input gradient, every parameter gradient and the BatchNorm running
+statistics must agree (same kernels underneath; the only differences are the summation order of the atomics in the
+weight-gradient / few-row kernels and of gradient merges)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu_path
+from test_gpu_sparse import _batch, _scene, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(net, coords, x, g, dev, direct_grads):
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p) if direct_grads else None
+    xin = _batch(coords, x, dev)
+    xin.x.requires_grad_(True)
+    out = net(xin).x
+    out.backward(g)
+    grads = {n: p.grad.detach().clone() for n, p in net.named_parameters()}
+    return out.detach().clone(), xin.x.grad.detach().clone(), grads
+
+
+@pytest.mark.parametrize("which,training,direct", [("two_level", True, True), ("two_level", False, False),
+                                                   ("paper", True, True), ("paper", True, False), ("paper", False, True)])
+def test_fastpath_matches_module_path(cuda_device, monkeypatch, which, training, direct):
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb, fastpath
+    torch.manual_seed(7)
+    cfg = bb.two_level_config(16) if which == "two_level" else bb.paper_backbone_config(16)
+    net = bb.Minkowski("unet", input_nc=4, config=cfg).to(cuda_device)
+    net.train(training)
+    assert fastpath.program_for(net) is not None
+    rng = np.random.default_rng(5)
+    coords = _scene(9, n=14000 if which == "paper" else 7000, extent=64)
+    x = rng.standard_normal((len(coords), 4)).astype(np.float32)
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.uniform_(-0.1, 0.1)
+                m.running_var.uniform_(0.8, 1.2)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    n_out = cfg["up_conv"]["up_conv_nn"][-1][-1]
+    g = torch.from_numpy(rng.standard_normal((len(coords), 16)).astype(np.float32)).to(cuda_device)
+
+    monkeypatch.setattr(fastpath, "ENABLED", False)
+    out_m, dx_m, gr_m = _run(net, coords, x, g, cuda_device, direct)
+    sd_m = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net.load_state_dict(sd0)
+    monkeypatch.setattr(fastpath, "ENABLED", True)
+    calls = []
+    orig = fastpath._UNetFn.apply
+    monkeypatch.setattr(fastpath._UNetFn, "apply", lambda *a: (calls.append(1), orig(*a))[1])
+    out_f, dx_f, gr_f = _run(net, coords, x, g, cuda_device, direct)
+    assert calls, "the fused executor did not run"
+    sd_f = net.state_dict()
+
+    def close(a, b, tol):
+        scale = max(float(b.abs().max()), 1e-6)
+        return float((a - b).abs().max()) <= tol * scale
+
+    def cos(a, b):
+        a, b = a.double().reshape(-1), b.double().reshape(-1)
+        return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+    assert close(out_f, out_m, 2e-5)
+    if training and which == "paper":
+        # batch statistics over the 50-row coarsest levels amplify the summation-order noise of the atomics (and flip
+        # ReLU masks of elements within rounding of zero): same bound as the module-path test against the oracle
+        assert cos(dx_f, dx_m) >= 0.9999
+        ga = torch.cat([gr_f[k].reshape(-1) for k in gr_m])
+        gb = torch.cat([gr_m[k].reshape(-1) for k in gr_m])
+        assert cos(ga, gb) >= 0.9999
+        for name in gr_m:
+            assert cos(gr_f[name], gr_m[name]) >= 0.995, name
+    else:
+        assert close(dx_f, dx_m, 2e-4)
+        for name in gr_m:
+            assert close(gr_f[name], gr_m[name], 5e-4), name
+    for k in sd_m:
+        if "running" in k:
+            assert close(sd_f[k], sd_m[k], 1e-5), k
+        if "num_batches_tracked" in k:
+            assert int(sd_f[k]) == int(sd_m[k])
+
+    # and against the functional CPU restatement (forward, 1e-4: north_star)
+    net.load_state_dict(sd0)
+    with torch.no_grad():
+        out_e = net(_batch(coords, x, cuda_device)).x
+    ref = cpu_path.unet_forward({k: v.cpu() for k, v in sd0.items()}, cpu_path.resolve_cfg(cfg, 4), torch.from_numpy(x),
+                                coords, training=training)
+    assert float((out_e.cpu() - ref).abs().max()) <= TOL * max(float(ref.abs().max()), 1.0)
+
+
+def test_fastpath_falls_back_on_foreign_modules(cuda_device):
+    """A module tree the tape compiler does not know runs through the module path (still CUDA kernels)."""
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb, fastpath, me
+    net = bb.Minkowski("unet", input_nc=4, config=bb.two_level_config(16)).to(cuda_device)
+    net.down_modules[0].conv_in[2] = me.MinkowskiLeakyReLU(0.1)
+    assert fastpath.program_for(net) is None
+    coords = _scene(1, n=3000)
+    x = np.random.default_rng(0).standard_normal((len(coords), 4)).astype(np.float32)
+    out = net(_batch(coords, x, cuda_device)).x
+    assert out.shape == (len(coords), 16) and bool(torch.isfinite(out).all())

@@ -261,7 +261,8 @@ def test_unet_forward_backward_parity(cuda_device, which, training, monkeypatch)
     within rounding of zero legitimately flip between two fp32 implementations and BatchNorm over the few
     rows of the coarsest levels amplifies that (fp32 CPU vs fp64 CPU differ by 1e-1 on the same test)."""
     me = _me()
-    from panopticsegforlargescalepointcloud_b200 import backbone as bb
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb, fastpath
+    monkeypatch.setattr(fastpath, "ENABLED", False)   # this test instruments the per-layer module path
     torch.manual_seed(2022)
     cfg = bb.two_level_config(16) if which == "two_level" else bb.paper_backbone_config(16)
     net = bb.Minkowski("unet", input_nc=4, config=cfg).to(cuda_device)
