@@ -112,11 +112,11 @@ int pgs_conv_fwd(const float* X, const float* W, const int32_t* nbr, int64_t n_q
 
 /* Occupancy-sorted gather table for the tensor-core conv kernels.  Those kernels skip every (16- or 128-row tile,
  * kernel offset) pair without a neighbour; rows in arbitrary order leave almost none (a 16-row union has ~26 of 27
- * offsets although a row has 2..13).  pgs_kmap_row_masks writes the per-offset pair counts (counts[K]) and one
- * K-bit occupancy mask per row (rarest offset = most significant bit); the caller sorts the masks (stable) to get
- * `order`, and pgs_kmap_permute writes nbr_sorted[k][r] = nbr[k][order[r]].  Passing (nbr_sorted, order) to a
- * tensor-core entry point gives bit-identical results to (nbr, NULL): tile row r is output row order[r]. */
-int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* counts, int64_t* masks, void* stream);
+ * offsets although a row has 2..13).  pgs_kmap_row_masks writes one K-bit occupancy mask per row (K <= 31; bit order:
+ * centre, faces, edges, corners = most significant); the caller sorts the masks (stable) to get `order`, and
+ * pgs_kmap_permute writes nbr_sorted[k][r] = nbr[k][order[r]].  Passing (nbr_sorted, order) to a tensor-core entry
+ * point gives the same rows as (nbr, NULL): tile row r is output row order[r]. */
+int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* masks, void* stream);
 int pgs_kmap_permute(const int32_t* nbr, int64_t n_q, int32_t K, const int32_t* order, int32_t* nbr_sorted,
                      void* stream);
 

@@ -54,7 +54,7 @@ SIGNATURES = {
     "pgs_conv_fwd_mma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pgs_conv_mma_split_supported": (c_int, [c_int32, c_int32]),
-    "pgs_kmap_row_masks": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgs_kmap_row_masks": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "pgs_kmap_permute": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgs_conv_fwd_mma_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -162,37 +162,33 @@ __global__ void __launch_bounds__(kThreads) pairs_emit_kernel(
 // offset = most significant bit) makes the rows of a tile share their empty offsets: the union drops to ~11 of 27
 // for the stride-1 maps and to ~2.4 for the transposed (up-sampling) maps, whose masks are parity classes.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) kmap_counts_kernel(const int32_t* __restrict__ nbr, int64_t n_q,
-                                                               int32_t* __restrict__ counts) {
-  const int k = blockIdx.y;
-  int c = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += (int64_t)gridDim.x * blockDim.x)
-    c += nbr[(int64_t)k * n_q + i] >= 0;
-#pragma unroll
-  for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[k], c);
-}
-
 __global__ void __launch_bounds__(kThreads) kmap_masks_kernel(const int32_t* __restrict__ nbr, int64_t n_q, int K,
-                                                              const int32_t* __restrict__ counts,
-                                                              int64_t* __restrict__ masks) {
-  __shared__ int bitpos[64];
-  if (threadIdx.x < K) {   // position of offset k in the order (count descending, k ascending): commonest -> bit 0
-    const int k = threadIdx.x, ck = counts[k];
+                                                              int ksize, int32_t* __restrict__ masks) {
+  // bit position of offset k: offsets ordered by (number of non-zero components, k) -- centre = bit 0, then the 6
+  // faces, the 12 edges, the 8 corners (the rarest neighbours) in the most significant bits; measured as good as
+  // ordering by the actual pair counts (profiles/r1_mask_order.txt) without a counting pass
+  __shared__ int bitpos[32];
+  if (threadIdx.x < K) {
+    const int half = (ksize & 1) ? ksize / 2 : 0;
+    auto nz = [&](int k) {
+      const int ix = k % ksize - half, iy = (k / ksize) % ksize - half, iz = k / (ksize * ksize) - half;
+      return (ix != 0) + (iy != 0) + (iz != 0);
+    };
+    const int k = threadIdx.x, mine = nz(k);
     int pos = 0;
     for (int j = 0; j < K; ++j) {
-      const int cj = counts[j];
-      pos += (cj > ck) || (cj == ck && j < k);
+      const int o = nz(j);
+      pos += (o < mine) || (o == mine && j < k);
     }
     bitpos[k] = pos;
   }
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_q) return;
-  uint64_t m = 0;
+  uint32_t m = 0;
   for (int k = 0; k < K; ++k)
-    if (nbr[(int64_t)k * n_q + i] >= 0) m |= 1ull << bitpos[k];
-  masks[i] = (int64_t)m;
+    if (nbr[(int64_t)k * n_q + i] >= 0) m |= 1u << bitpos[k];
+  masks[i] = (int32_t)m;
 }
 
 __global__ void __launch_bounds__(kThreads) kmap_permute_kernel(const int32_t* __restrict__ nbr, int64_t n_q,
@@ -309,16 +305,14 @@ int pgs_kmap_pairs(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* in_idx, 
   return PGS_OK;
 }
 
-int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* counts, int64_t* masks, void* stream) {
-  PGS_CHECK_ARG(K >= 1 && K <= 63, "kernel volume must be in 1..63");
-  cudaStream_t s = (cudaStream_t)stream;
-  PGS_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * K, s));
+int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* masks, void* stream) {
+  PGS_CHECK_ARG(K >= 1 && K <= 31, "kernel volume must be in 1..31");
   if (n_q == 0) return PGS_OK;
-  int gx = grid_for(n_q);
-  if (gx > kNumSM * 4) gx = kNumSM * 4;
-  kmap_counts_kernel<<<dim3(gx, K), kThreads, 0, s>>>(nbr, n_q, counts);
-  kmap_masks_kernel<<<grid_for(n_q), kThreads, 0, s>>>(nbr, n_q, K, counts, masks);
-  count_launch(2);
+  int ksize = 1;
+  while (ksize * ksize * ksize < K) ++ksize;
+  PGS_CHECK_ARG(ksize * ksize * ksize == K, "kernel volume must be a cube");
+  kmap_masks_kernel<<<grid_for(n_q), kThreads, 0, (cudaStream_t)stream>>>(nbr, n_q, K, ksize, masks);
+  count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;
 }

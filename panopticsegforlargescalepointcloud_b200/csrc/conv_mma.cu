@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) conv_mma_prep_weights_kernel(const float*
 // WS = 0: weights of one kernel offset staged in shared memory (cp.async double buffer, one barrier per offset)
 // WS = 1: weight fragments read straight from global memory (L1-resident for the small shapes), no barrier
 template <int CIN, int COUT, int MT, int WS>
-__global__ void __launch_bounds__(kMmThreads, (CIN * COUT <= 32 * 32 ? 2 : 1)) conv_mma_kernel(const float* __restrict__ X, const float4* __restrict__ Wf,
+__global__ void __launch_bounds__(kMmThreads, (CIN * COUT * MT <= 32 * 32 ? 2 : 1)) conv_mma_kernel(const float* __restrict__ X, const float4* __restrict__ Wf,
                                                                const int32_t* __restrict__ nbr, int64_t n_q, int K,
                                                                int mirror, const int32_t* __restrict__ order,
                                                                float* __restrict__ Y) {
@@ -360,7 +360,8 @@ static int launch_mma(const float* X, const float* Wf, const int32_t* nbr, const
 template <int CIN, int COUT>
 static int launch_mma_shape(const float* X, const float* Wf, const int32_t* nbr, const int32_t* order, int64_t n_q,
                             int K, int mirror, float* Y, int ws, int mt, cudaStream_t s) {
-  constexpr bool kTwo = (CIN <= 32 && COUT <= 32);   // two m-tiles per warp fit the register file
+  // two m-tiles per warp (weight fragments reused) where they fit 128 registers; 32 x 32 needs 166 -> one m-tile
+  constexpr bool kTwo = (CIN * COUT <= 32 * 16);
   if (kTwo && mt != 1) {
     if (ws) return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 1>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
     return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 0>(X, Wf, nbr, order, n_q, K, mirror, Y, s);

@@ -57,9 +57,8 @@ class KernelMap:
         if self._sorted is None:
             lib = _lib.load()
             dev = self.nbr.device
-            counts = torch.empty(self.K, dtype=torch.int32, device=dev)
-            masks = torch.empty(max(self.n_q, 1), dtype=torch.int64, device=dev)
-            check(lib.pgs_kmap_row_masks(ptr(self.nbr), self.n_q, self.K, ptr(counts), ptr(masks), stream_ptr()))
+            masks = torch.empty(max(self.n_q, 1), dtype=torch.int32, device=dev)
+            check(lib.pgs_kmap_row_masks(ptr(self.nbr), self.n_q, self.K, ptr(masks), stream_ptr()))
             order = torch.sort(masks[:self.n_q], stable=True)[1].to(torch.int32)
             nbr_sorted = torch.empty_like(self.nbr)
             check(lib.pgs_kmap_permute(ptr(self.nbr), self.n_q, self.K, ptr(order), ptr(nbr_sorted), stream_ptr()))

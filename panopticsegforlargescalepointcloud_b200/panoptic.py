@@ -221,7 +221,10 @@ class BaseModel(nn.Module):
     def optimize_parameters2(self, epoch, step, batch_size):
         """base_model.py:259-285: forward, zero_grad, backward, (clip), optimizer step."""
         self.forward(epoch=epoch, step=step, is_training=True)
-        self._optimizer.zero_grad(set_to_none=False)
+        if getattr(self, "_zero_grad_hook", None) is not None:
+            self._zero_grad_hook()
+        else:
+            self._optimizer.zero_grad(set_to_none=False)
         self.backward(epoch)
         _me.join_side_stream()   # weight-gradient kernels run on a side stream (me.DW_DIRECT)
         if self._grad_hook is not None:

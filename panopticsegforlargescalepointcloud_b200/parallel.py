@@ -46,9 +46,12 @@ class FlatGradBucket:
         dev, dt = self.params[0].device, torch.float32
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=dt, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            self.views.append(v)
             off += p.numel()
 
     def zero(self):
@@ -56,15 +59,15 @@ class FlatGradBucket:
 
     def check_views(self):
         """Some optimisers / zero_grad(set_to_none=True) drop .grad; re-attach the views."""
-        off = 0
-        for p in self.params:
-            v = self.flat[off:off + p.numel()].view_as(p)
-            if p.grad is None:
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is v:
+                continue
+            if g is None:
                 p.grad = v
-            elif p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
                 p.grad = v
-            off += p.numel()
 
     def all_reduce_mean(self, world=None):
         if dist.is_initialized() and dist.get_world_size() > 1:
@@ -84,6 +87,7 @@ class DataParallelStep:
                 for t in list(model.parameters()) + list(model.buffers()):
                     dist.broadcast(t, src=0)
         model._grad_hook = self._hook
+        model._zero_grad_hook = self.bucket.zero   # one memset of the flat buffer instead of one fill per parameter
 
     def _hook(self):
         self.bucket.check_views()
