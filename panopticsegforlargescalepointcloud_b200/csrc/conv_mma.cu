@@ -253,6 +253,187 @@ __global__ void __launch_bounds__(kMmThreads, (CIN * COUT * MT <= 32 * 32 ? 2 : 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Queued variant (used for the narrowest shapes, CIN * COUT <= 512, where it measured 20-30 % faster; from 32 x 32 on
+// the register version is ahead by ~10 %): the gathered rows travel global -> shared memory with cp.async into a per-THREAD ring of
+// D kernel offsets (each lane later reads back exactly the 16-byte pieces it copied, so no cross-lane
+// synchronisation is needed for them), the weight fragments of an offset ride in the same cp.async group.  Compared
+// with conv_mma_kernel (register double buffer, depth 1) this frees the prefetch registers -- 16 x 16 drops to one
+// m-tile per warp at <= 64 registers, 4 CTAs = 32 warps per SM instead of 16 -- and keeps D - 1 offsets of loads in
+// flight per thread: ncu of the register version showed 23 % of warp slots active and long-scoreboard (gather
+// latency) as the top stall at 24 % tensor-pipe activity (profiles/r1_conv_mma_ncu.txt).
+// Missing neighbours are zero-filled by cp.async itself (src-size 0).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+               "r"(sz)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int CIN, int COUT, int D, int MINB>
+__global__ void __launch_bounds__(kMmThreads, MINB) conv_mmaq_kernel(const float* __restrict__ X,
+                                                                      const float4* __restrict__ Wf,
+                                                                      const int32_t* __restrict__ nbr, int64_t n_q, int K,
+                                                                      int mirror, const int32_t* __restrict__ order,
+                                                                      float* __restrict__ Y) {
+  constexpr int R = kMmWarps * 16;        // rows per CTA (one 16-row m-tile per warp)
+  constexpr int J = CIN / 8, NT = COUT / 8, F4 = CIN / 16;
+  constexpr int WSTAGE = J * NT * 32;     // float4 elements of one offset's weight fragments
+  constexpr int QSLOT = 2 * F4;           // float4 pieces per thread and offset (rows g and g + 8)
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  int* idx = (int*)smem_raw;                                                     // [K][R]
+  float4* wst = (float4*)(smem_raw + (size_t)kMmMaxK * R * 4);                   // [D][WSTAGE]
+  float4* que = wst + (size_t)D * WSTAGE;                                        // [D][QSLOT][kMmThreads]
+  __shared__ int klist[kMmMaxK];
+  __shared__ unsigned kmask_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  if (tid == 0) kmask_s = 0u;
+  __syncthreads();
+  {
+    unsigned mine = 0u;
+    for (int e = tid; e < K * R; e += kMmThreads) {
+      const int k = e / R, r = e - k * R;
+      const int64_t row = row0 + r;
+      int v = -1;
+      if (row < n_q) v = __ldg(&nbr[(int64_t)k * n_q + row]);
+      idx[e] = v;
+      if (v >= 0) mine |= 1u << k;
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, sft);
+    if (lane == 0 && mine) atomicOr(&kmask_s, mine);
+  }
+  __syncthreads();
+  int n_off = 0;
+  {
+    const unsigned km = kmask_s;
+    for (int k = 0; k < K; ++k) {   // weight index order; table offset tk = mirror ? K-1-k : k
+      const int tk = mirror ? (K - 1 - k) : k;
+      if (km & (1u << tk)) {
+        if (tid == 0) klist[n_off] = k;
+        ++n_off;
+      }
+    }
+  }
+  __syncthreads();
+
+  float accm[NT][4], accc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) accm[n][c] = accc[n][c] = 0.f;
+
+  // group G_o = rows + weights of the o-th non-empty offset (an empty group past the end keeps the counting uniform)
+  auto issue = [&](int o) {
+    if (o < n_off) {
+      const int k = klist[o];
+      const int tk = mirror ? (K - 1 - k) : k;
+      const int st = o % D;
+      const int* col = idx + tk * R + warp * 16 + g;
+      const int s0 = col[0], s1 = col[8];
+      float4* q = que + (size_t)st * QSLOT * kMmThreads + tid;
+      const float4* x0 = (const float4*)(X + (size_t)(s0 >= 0 ? s0 : 0) * CIN) + t;
+      const float4* x1 = (const float4*)(X + (size_t)(s1 >= 0 ? s1 : 0) * CIN) + t;
+#pragma unroll
+      for (int i = 0; i < F4; ++i) {
+        cp_async16_zfill(q + (size_t)(2 * i) * kMmThreads, x0 + 4 * i, s0 >= 0);
+        cp_async16_zfill(q + (size_t)(2 * i + 1) * kMmThreads, x1 + 4 * i, s1 >= 0);
+      }
+      const float4* wsrc = Wf + (size_t)k * WSTAGE;
+      float4* wdst = wst + (size_t)st * WSTAGE;
+      for (int e = tid; e < WSTAGE; e += kMmThreads) cp_async16(wdst + e, wsrc + e);
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int o = 0; o < D - 1; ++o) issue(o);
+  for (int o = 0; o < n_off; ++o) {
+    cp_async_wait<D - 2>();   // G_o has landed (at most the D - 2 younger groups are still in flight)
+    __syncthreads();          // ... for every thread; and everyone is done with the slot G_{o+D-1} overwrites
+    issue(o + D - 1);
+    const int k = klist[o];
+    const int tk = mirror ? (K - 1 - k) : k;
+    const int* col = idx + tk * R + warp * 16 + g;
+    if (!__any_sync(0xffffffffu, (col[0] >= 0) | (col[8] >= 0))) continue;   // this warp's 16 rows: no neighbour
+    const int st = o % D;
+    const float4* q = que + (size_t)st * QSLOT * kMmThreads + tid;
+    const float4* wb = wst + (size_t)st * WSTAGE + lane;
+#pragma unroll
+    for (int i = 0; i < F4; ++i) {
+      const float4 v0 = q[(size_t)(2 * i) * kMmThreads], v1 = q[(size_t)(2 * i + 1) * kMmThreads];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        uint32_t ahi[4], alo[4];
+        split_tf32_fast(jj ? v0.z : v0.x, ahi[0], alo[0]);
+        split_tf32_fast(jj ? v1.z : v1.x, ahi[1], alo[1]);
+        split_tf32_fast(jj ? v0.w : v0.y, ahi[2], alo[2]);
+        split_tf32_fast(jj ? v1.w : v1.y, ahi[3], alo[3]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const float4 b = wb[((2 * i + jj) * NT + n) * 32];
+          const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
+          mma_tf32(accm[n], ahi, bh0, bh1);
+          mma_tf32(accc[n], alo, bh0, bh1);
+          mma_tf32(accc[n], ahi, __float_as_uint(b.z), __float_as_uint(b.w));
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: lane (g, t) owns channels 16 m + 4 t .. +3 of rows g and g + 8
+  const int64_t t0 = row0 + warp * 16 + g, t1 = t0 + 8;   // rows of the (sorted) table
+  const bool ok0 = t0 < n_q, ok1 = t1 < n_q;
+  const int64_t r0 = (ok0 && order) ? (int64_t)__ldg(&order[t0]) : t0;   // output rows
+  const int64_t r1 = (ok1 && order) ? (int64_t)__ldg(&order[t1]) : t1;
+#pragma unroll
+  for (int m = 0; m < NT / 2; ++m) {
+    const int c = 16 * m + 4 * t;
+    if (ok0)
+      *(float4*)(Y + (size_t)r0 * COUT + c) =
+          make_float4(accm[2 * m][0] + accc[2 * m][0], accm[2 * m][1] + accc[2 * m][1],
+                      accm[2 * m + 1][0] + accc[2 * m + 1][0], accm[2 * m + 1][1] + accc[2 * m + 1][1]);
+    if (ok1)
+      *(float4*)(Y + (size_t)r1 * COUT + c) =
+          make_float4(accm[2 * m][2] + accc[2 * m][2], accm[2 * m][3] + accc[2 * m][3],
+                      accm[2 * m + 1][2] + accc[2 * m + 1][2], accm[2 * m + 1][3] + accc[2 * m + 1][3]);
+  }
+}
+
+template <int CIN, int COUT>
+static int launch_mmaq(const float* X, const float* Wf, const int32_t* nbr, const int32_t* order, int64_t n_q, int K,
+                       int mirror, float* Y, cudaStream_t s) {
+  // ring depth and CTAs per SM from the shared memory of one ring stage (weight fragments + per-thread row pieces)
+  constexpr int STAGE = CIN * COUT * 8 + CIN * 512;
+  constexpr int D = (STAGE <= 12 * 1024) ? 4 : (STAGE <= 30 * 1024 ? 3 : 2);
+  constexpr int FIT = (224 * 1024) / (kMmMaxK * kMmWarps * 16 * 4 + D * STAGE + 1024);
+  constexpr int RCAP = COUT <= 16 ? 4 : (COUT <= 32 ? 3 : 2);   // 2 * COUT accumulator registers per thread
+  constexpr int MINB = FIT < 1 ? 1 : (FIT > RCAP ? RCAP : FIT);
+  constexpr int R = kMmWarps * 16;
+  constexpr size_t smem = (size_t)kMmMaxK * R * 4 +
+                          (size_t)D * ((size_t)(CIN / 8) * (COUT / 8) * 32 * 16 + (size_t)2 * (CIN / 16) * kMmThreads * 16);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PGS_CUDA(cudaFuncSetAttribute(conv_mmaq_kernel<CIN, COUT, D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    PGS_CUDA(cudaFuncSetAttribute(conv_mmaq_kernel<CIN, COUT, D, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  const unsigned gx = (unsigned)((n_q + R - 1) / R);
+  conv_mmaq_kernel<CIN, COUT, D, MINB><<<gx, kMmThreads, smem, s>>>(X, (const float4*)Wf, nbr, n_q, K, mirror, order, Y);
+  return PGS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Few-row layers (coarse U-Net levels: 50 .. a few thousand rows, 64 .. 192 channels).  These launches are latency
 // bound, not throughput bound: the whole layer is a few MFLOP but the weights are up to 4 MB.  Work item of one
 // WARP = (16-row tile, 16 output channels, one part of the kernel offsets); no shared memory, no barrier; the
@@ -363,10 +544,8 @@ static int launch_mma_shape(const float* X, const float* Wf, const int32_t* nbr,
   // two m-tiles per warp (weight fragments reused) where they fit 128 registers; 32 x 32 needs 166 -> one m-tile
   constexpr bool kTwo = (CIN * COUT <= 32 * 16);
   if (kTwo && mt != 1) {
-    if (ws) return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 1>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
     return launch_mma<CIN, COUT, (kTwo ? 2 : 1), 0>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
   }
-  if (ws) return launch_mma<CIN, COUT, 1, 1>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
   return launch_mma<CIN, COUT, 1, 0>(X, Wf, nbr, order, n_q, K, mirror, Y, s);
 }
 
@@ -395,8 +574,10 @@ int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, const i
   if (n_q == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   float* Wf = (float*)scratch;
-  static int ws = -1, mt = -1;
+  static int ws = -1, mt = -1, queued = 1;
   if (ws < 0) {
+    const char* q = getenv("PGS_MMA_QUEUE");  // "0": register double-buffer version (conv_mma_kernel)
+    queued = !(q && q[0] == '0');
     const char* e = getenv("PGS_MMA_WSRC");   // "ldg": weight fragments straight from global / L1 (experiment)
     ws = (e && e[0] == 'l') ? 1 : 0;
     const char* m = getenv("PGS_MMA_MT");     // "1": one m-tile per warp everywhere (experiment)
@@ -409,7 +590,8 @@ int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, const i
   int rc = PGS_ERR_INVALID;
 #define PGS_MMA_CASE(CI, CO)                                                                   \
   case CI * 1000 + CO:                                                                         \
-    rc = launch_mma_shape<CI, CO>(X, Wf, nbr, order, n_q, K, mirror, Y, ws, mt, s);                   \
+    rc = (queued && CI * CO <= 32 * 16) ? launch_mmaq<CI, CO>(X, Wf, nbr, order, n_q, K, mirror, Y, s) \
+                : launch_mma_shape<CI, CO>(X, Wf, nbr, order, n_q, K, mirror, Y, ws, mt, s);     \
     break;
   switch (c_in * 1000 + c_out) {
     PGS_MMA_CASE(16, 16) PGS_MMA_CASE(16, 32) PGS_MMA_CASE(16, 48) PGS_MMA_CASE(16, 64)

@@ -300,7 +300,8 @@ def conv_algorithmic_bytes(n_in, n_out, K, c_in, c_out, has_table):
 # kernel splits their kernel offsets over CTAs.  (csrc/conv_mma.cu; measured per shape in profiles/)
 MMA_MIN_ROWS = int(_os.environ.get("PGS_MMA_MIN_ROWS", "8192"))
 SPLIT_MAX_ROWS = int(_os.environ.get("PGS_SPLIT_MAX_ROWS", "2048"))
-MMA_MAX_CH = int(_os.environ.get("PGS_MMA_MAX_CH", "64"))
+MMA_MAX_CH = int(_os.environ.get("PGS_MMA_MAX_CH", "64"))       # c_in bound
+MMA_MAX_COUT = int(_os.environ.get("PGS_MMA_MAX_COUT", "32"))   # measured: tcgen05 wins from 48 output channels on
 
 
 def _conv_kernel_choice(lib, K, c_in, c_out, n_q, has_table):
@@ -313,7 +314,7 @@ def _conv_kernel_choice(lib, K, c_in, c_out, n_q, has_table):
     mma_ok = (has_table and K <= 27 and max(c_in, c_out) <= MMA_MAX_CH and lib.pgs_conv_mma_supported(c_in, c_out))
     if CONV_IMPL == "mma" and mma_ok:
         return "mma"
-    if CONV_IMPL == "auto" and mma_ok and n_q >= MMA_MIN_ROWS:
+    if CONV_IMPL == "auto" and mma_ok and n_q >= MMA_MIN_ROWS and c_out <= MMA_MAX_COUT:
         return "mma"
     if K <= 27 and c_out > SMALL_COUT and lib.pgs_conv_tc_supported(c_in, c_out):
         return "tc"

@@ -80,18 +80,18 @@ for lv, cin, cout, alt in cases:
     rec["alt"] = alt
     for impl in ("tc", alt):
         me.CONV_IMPL = impl
-        Y = me._conv_fwd_raw(X, W, km.nbr, n_out, 0, 0)
-        Ym = me._conv_fwd_raw(X, Wt, km.nbr, n_out, 1, 1)   # mirrored + transposed-weights launch (input-gradient form)
+        Y = me._conv_fwd_raw(X, W, km, n_out, 0, 0)
+        Ym = me._conv_fwd_raw(X, Wt, km, n_out, 1, 1)   # mirrored + transposed-weights launch (input-gradient form)
         torch.cuda.synchronize()
         res[impl] = (Y, Ym)
         if ref is not None:
             rec["err_%s_vs_fp64" % ("tc" if impl == "tc" else "alt")] = float(np.abs(Y[:ref.shape[0]].cpu().numpy() - ref).max())
         for _ in range(3):
-            me._conv_fwd_raw(X, W, km.nbr, n_out, 0, 0)
+            me._conv_fwd_raw(X, W, km, n_out, 0, 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            me._conv_fwd_raw(X, W, km.nbr, n_out, 0, 0)
+            me._conv_fwd_raw(X, W, km, n_out, 0, 0)
         e1.record(); torch.cuda.synchronize()
         rec["us_%s" % ("tc" if impl == "tc" else "alt")] = e0.elapsed_time(e1) * 100
     rec["scale"] = float(res["tc"][0].abs().max())
