@@ -157,6 +157,14 @@ int pgs_conv_bwd_weight(const float* X, const float* dY,
                         int64_t max_pairs, int32_t K, int32_t c_in, int32_t c_out, int32_t mirror,
                         float* dW, void* stream);
 
+/* Tensor-core weight gradient (mma.sync tf32, 3-product split, pair rows loaded straight into the fragments);
+ * pgs_conv_bwd_weight forwards to it when both channel counts are multiples of 16 (PGS_DW_IMPL=ffma disables). */
+int pgs_conv_dw_mma_supported(int32_t c_in, int32_t c_out);
+int pgs_conv_bwd_weight_mma(const float* X, const float* dY,
+                            const int32_t* in_idx, const int32_t* out_idx, const int32_t* offs,
+                            int64_t max_pairs, int32_t K, int32_t c_in, int32_t c_out, int32_t mirror,
+                            float* dW, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Ball query + region growing  (replaces torch_points_kernels.ball_query(mode="PARTIAL_DENSE") and
  *                               torch_points_kernels.region_grow -- un-vendored dependency, tpk 0.7.0;

@@ -62,6 +62,9 @@ SIGNATURES = {
                                c_float, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_bn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                 c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgs_conv_dw_mma_supported": (c_int, [c_int32, c_int32]),
+    "pgs_conv_bwd_weight_mma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                        c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "pgs_bn_forward_ex": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                   c_float, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_bn_backward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,

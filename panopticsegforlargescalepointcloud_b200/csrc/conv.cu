@@ -11,6 +11,8 @@
 // scatter-add, deterministic).  Offsets for which no row of the tile has a neighbour are
 // skipped with one block-wide vote.  fp32 FFMA math: the parity bar is 1e-4 against an fp32
 // oracle, which rules out single-pass tf32/bf16 tensor-core math.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pgs {
@@ -438,6 +440,13 @@ int pgs_conv_bwd_weight(const float* X, const float* dY, const int32_t* in_idx, 
   if (max_pairs <= 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   PGS_CHECK_ARG(c_in % 4 == 0 && c_out % 4 == 0, "channel counts must be multiples of 4 (16-byte row chunks)");
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("PGS_DW_IMPL");   // "ffma": always the fp32 FFMA kernel below
+    use_mma = !(e && e[0] == 'f');
+  }
+  if (use_mma && pgs_conv_dw_mma_supported(c_in, c_out))   // tensor-core version (conv_dw_mma.cu)
+    return pgs_conv_bwd_weight_mma(X, dY, in_idx, out_idx, offs, max_pairs, K, c_in, c_out, mirror, dW, stream);
   const int tci = (c_in % 32 == 0) ? 32 : (c_in % 16 == 0 ? 16 : 4);
   const int tco = (c_out % 32 == 0) ? 32 : 16;
   const int n_ci = (c_in + tci - 1) / tci, n_co = (c_out + tco - 1) / tco;
