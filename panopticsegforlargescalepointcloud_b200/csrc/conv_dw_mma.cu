@@ -32,6 +32,24 @@ __device__ __forceinline__ void dm_mma(float (&d)[4], const uint32_t (&a)[4], ui
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// correction products lo*hi + hi*lo in ONE bf16 m16n8k16 MMA (see mma_corr in conv_mma.cu): contraction slots 2t / 2t+1
+// hold (x_lo, d_hi) of the lane's pairs t / t+4, slots 2t+8 / 2t+9 hold (x_hi, d_lo) of the same pairs
+__device__ __forceinline__ uint32_t dm_pack(uint32_t first_bits, uint32_t second_bits) {   // first -> low half
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(second_bits)), "f"(__uint_as_float(first_bits)));
+  return d;
+}
+__device__ __forceinline__ void dm_corr(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
+                                        const uint32_t (&bhi)[2], const uint32_t (&blo)[2]) {
+  const uint32_t a0 = dm_pack(alo[0], alo[2]), a1 = dm_pack(alo[1], alo[3]);
+  const uint32_t a2 = dm_pack(ahi[0], ahi[2]), a3 = dm_pack(ahi[1], ahi[3]);
+  const uint32_t b0 = dm_pack(bhi[0], bhi[1]), b1 = dm_pack(blo[0], blo[1]);
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 // MT m-tiles of 16 input channels, NT n-tiles of 8 output channels per CTA tile
 template <int MT, int NT>
 __global__ void __launch_bounds__(kDmThreads) conv_dw_mma_kernel(
@@ -109,8 +127,7 @@ __global__ void __launch_bounds__(kDmThreads) conv_dw_mma_kernel(
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
           dm_mma(accm[m][n], ahi[m], bhi[n][0], bhi[n][1]);
-          dm_mma(accc[m][n], alo[m], bhi[n][0], bhi[n][1]);
-          dm_mma(accc[m][n], ahi[m], blo[n][0], blo[n][1]);
+          dm_corr(accc[m][n], ahi[m], alo[m], bhi[n], blo[n]);
         }
     }
   }

@@ -15,8 +15,8 @@
 // kernel offset (for the shared weight stage) instead of one per 16 channels, and empty (16-row tile, offset)
 // pairs are skipped.
 //
-// Precision: identical scheme to conv_tc.cu -- operands split a = hi + lo (round-to-nearest tf32), hi*hi
-// accumulates in one fp32 fragment, lo*hi + hi*lo in a second one, summed in the epilogue.
+// Precision: operands split a = hi + lo (hi = round-to-nearest tf32); hi*hi accumulates in one fp32 fragment (tf32
+// MMA), lo*hi + hi*lo in a second one (one bf16 m16n8k16 MMA, see mma_corr), summed in the epilogue.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -48,6 +48,25 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// Correction products on the bf16 path.  lo*hi + hi*lo are 2^-12 of the main product, so 8 mantissa bits are enough
+// for them (every rounding below contributes <= 2^-21 |x||w|, the size of the lo*lo term that is dropped anyway;
+// numpy emulation: max error 3e-6 at output scale 4 vs 3e-7, next to ~4e-6 from the tensor core's own accumulation).
+// ONE m16n8k16 bf16 MMA does both: contraction slots 0..7 hold (x_lo, w_hi), slots 8..15 hold (x_hi, w_lo) of the same
+// 8 channels -- slot 2t / 2t+1 <-> the lane's own channels c(j,t) / c(j,t+4), so no data moves between lanes.
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t first_bits, uint32_t second_bits) {   // first -> low half
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(second_bits)), "f"(__uint_as_float(first_bits)));
+  return d;
+}
+__device__ __forceinline__ void mma_corr(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint32_t bh,
+                                         uint32_t bl) {
+  const uint32_t a0 = pack_bf16(alo[0], alo[2]), a1 = pack_bf16(alo[1], alo[3]);
+  const uint32_t a2 = pack_bf16(ahi[0], ahi[2]), a3 = pack_bf16(ahi[1], ahi[3]);
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bh), "r"(bl));
+}
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
                : "memory");
@@ -63,7 +82,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // K-steps 2i and 2i+1):   K-step j, position p  <->  channel 16 (j/2) + 4 (p%4) + 2 (j%2) + p/4
 // Output permutation (so that a lane's c0,c1 of n-tiles 2m and 2m+1 are 4 consecutive channels):
 //   n-tile n, position q  <->  channel 16 (n/2) + 4 (q/2) + 2 (n%2) + q%2
-// Wf[k][j][n][lane] = float4(b0_hi, b1_hi, b0_lo, b1_lo)
+// Wf[k][j][n][lane] = float4(b0_hi, b1_hi, bf16x2(b0_hi, b1_hi), bf16x2(b0_lo, b1_lo))
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_mma_prep_weights_kernel(const float* __restrict__ W, int K, int C, int N,
                                                                      int w_transposed, float* __restrict__ Wf) {
@@ -85,10 +104,11 @@ __global__ void __launch_bounds__(256) conv_mma_prep_weights_kernel(const float*
       // !w_transposed: W stored [K][C][N];  w_transposed: W stored [K][N][C]
       v[h] = w_transposed ? W[((int64_t)k * N + co) * C + ci] : W[((int64_t)k * C + ci) * N + co];
     }
-    uint32_t h0, l0, h1, l1;
-    split_tf32(v[0], h0, l0);
-    split_tf32(v[1], h1, l1);
-    ((float4*)Wf)[e] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    const uint32_t h0 = tf32_rn_bits(v[0]), h1 = tf32_rn_bits(v[1]);
+    const uint32_t l0 = __float_as_uint(v[0] - __uint_as_float(h0)), l1 = __float_as_uint(v[1] - __uint_as_float(h1));
+    // (b0_hi, b1_hi) tf32 for the main MMA; bf16 pairs (hi, hi) and (lo, lo) = B fragment of the correction MMA
+    ((float4*)Wf)[e] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(pack_bf16(h0, h1)),
+                                   __uint_as_float(pack_bf16(l0, l1)));
   }
 }
 
@@ -203,8 +223,7 @@ __global__ void __launch_bounds__(kMmThreads, (CIN * COUT * MT <= 32 * 32 ? 2 : 
         for (int mt = 0; mt < MT; ++mt) {
           if (MT > 1 && !(vcur & (1u << mt))) continue;
           mma_tf32(accm[mt][n], ahi[mt], bh0, bh1);
-          mma_tf32(accc[mt][n], alo[mt], bh0, bh1);
-          mma_tf32(accc[mt][n], ahi[mt], bl0, bl1);
+          mma_corr(accc[mt][n], ahi[mt], alo[mt], bl0, bl1);
         }
       }
     }
@@ -381,8 +400,7 @@ __global__ void __launch_bounds__(kMmThreads, MINB) conv_mmaq_kernel(const float
           const float4 b = wb[((2 * i + jj) * NT + n) * 32];
           const uint32_t bh0 = __float_as_uint(b.x), bh1 = __float_as_uint(b.y);
           mma_tf32(accm[n], ahi, bh0, bh1);
-          mma_tf32(accc[n], alo, bh0, bh1);
-          mma_tf32(accc[n], ahi, __float_as_uint(b.z), __float_as_uint(b.w));
+          mma_corr(accc[n], ahi, alo, __float_as_uint(b.z), __float_as_uint(b.w));
         }
       }
     }
@@ -498,8 +516,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) conv_mma_split_kernel(const 
           const uint32_t bh0 = __float_as_uint(b[jj][n].x), bh1 = __float_as_uint(b[jj][n].y);
           const uint32_t bl0 = __float_as_uint(b[jj][n].z), bl1 = __float_as_uint(b[jj][n].w);
           mma_tf32(accm[n], ahi, bh0, bh1);
-          mma_tf32(accc[n], alo, bh0, bh1);
-          mma_tf32(accc[n], ahi, bl0, bl1);
+          mma_corr(accc[n], ahi, alo, bl0, bl1);
         }
       }
     }
