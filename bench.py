@@ -64,7 +64,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -170,12 +170,11 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / k, last, (t0, t1)
 
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~1 s to come up
     for i in range(args.warmup):
         step(i, False)
     for i in range(min(args.warmup, 2)):
         step(i, True)
-
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     prof = []
     ms_dev, last_dev, (t0, t1) = timed(args.steps, False, profile=prof)
@@ -204,9 +203,11 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = tot_b / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_note = {k: tj[k] for k in ("kernel", "algorithmic_bytes_same_launch") if k in tj}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "sparse-conv gather-GEMM launches, forward + input-gradient (pgs::conv_mma_kernel "
@@ -214,7 +215,8 @@ def run_b200(args):
                 "[few-row layers]); time per kernel kind in by_kernel_ms",
                 "achieved": achieved,
                 "peak": peak, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "launches": len(prof),
+                "frac": achieved / peak, "traffic": traffic, "traffic_of": traffic_note if traffic is not None else None,
+                "launches": len(prof),
                 "alg_bytes_per_launch": tot_b / max(len(prof), 1), "avg_launch_ms": tot_ms / max(len(prof), 1),
                 "conv_share_of_step": tot_ms / (ms_dev * args.steps)}
     by_kind = {}

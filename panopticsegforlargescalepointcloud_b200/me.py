@@ -301,7 +301,7 @@ def conv_algorithmic_bytes(n_in, n_out, K, c_in, c_out, has_table):
 MMA_MIN_ROWS = int(_os.environ.get("PGS_MMA_MIN_ROWS", "8192"))
 SPLIT_MAX_ROWS = int(_os.environ.get("PGS_SPLIT_MAX_ROWS", "2048"))
 MMA_MAX_CH = int(_os.environ.get("PGS_MMA_MAX_CH", "64"))       # c_in bound
-MMA_MAX_COUT = int(_os.environ.get("PGS_MMA_MAX_COUT", "32"))   # measured: tcgen05 wins from 48 output channels on
+MMA_MAX_COUT = int(_os.environ.get("PGS_MMA_MAX_COUT", "48"))   # measured: tcgen05 wins from 64 output channels on
 
 
 def _conv_kernel_choice(lib, K, c_in, c_out, n_q, has_table):
