@@ -123,7 +123,8 @@ int pgs_kmap_permute(const int32_t* nbr, int64_t n_q, int32_t K, const int32_t* 
 /* tcgen05 (5th-generation tensor core) variant of pgs_conv_fwd: same result contract, fp32 in / fp32 out,
  * 3-pass tf32 hi/lo split with fp32 accumulation in tensor memory.  Supported when
  * pgs_conv_tc_supported(c_in, c_out) (c_in % 16 == 0, c_out % 16 == 0, 16 <= c_out <= 192).
- * scratch holds the re-arranged weights (pgs_conv_tc_scratch_bytes). */
+ * scratch holds the re-arranged weights (pgs_conv_tc_scratch_bytes); W == NULL: scratch was filled by
+ * pgs_conv_prep_weights_batch (also accepted by pgs_conv_fwd_mma / pgs_conv_fwd_mma_split). */
 int pgs_conv_tc_supported(int32_t c_in, int32_t c_out);
 size_t pgs_conv_tc_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out);
 int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q,
@@ -148,6 +149,13 @@ int pgs_conv_mma_split_supported(int32_t c_in, int32_t c_out);
 int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q,
                            int32_t K, int32_t c_in, int32_t c_out, int32_t mirror, int32_t w_transposed,
                            float* Y, void* scratch, size_t scratch_bytes, void* stream);
+
+/* All weight re-arrangements of a pass in one launch (the fused executor prepares the forward and the backward
+ * layout of every convolution at the start of a step).  desc: device array of n_desc records of 8 int64:
+ * { W, dst, K, c_in, c_out, w_transposed, layout (0 = pgs_conv_fwd_tc, 1 = pgs_conv_fwd_mma / _split), 0 } with c_in /
+ * c_out as the conv entry point will see them; dst = the `scratch` later passed to that entry point together with
+ * W == NULL ("weights already arranged").  max_elems = largest K * c_in * c_out of the batch (sizes the grid). */
+int pgs_conv_prep_weights_batch(const int64_t* desc, int32_t n_desc, int64_t max_elems, void* stream);
 
 /* dW must be zeroed by the caller (accumulates).  in_idx/out_idx/offs (device) from pgs_kmap_pairs
  * of the FORWARD table; max_pairs = max_k (offs[k+1]-offs[k]) (host value, sizes the grid).

@@ -65,6 +65,7 @@ SIGNATURES = {
     "pgs_conv_dw_mma_supported": (c_int, [c_int32, c_int32]),
     "pgs_conv_bwd_weight_mma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                         c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "pgs_conv_prep_weights_batch": (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
     "pgs_bn_forward_ex": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                   c_float, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_bn_backward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "conv_prep.cuh"
 
 namespace pgs {
 
@@ -86,29 +87,26 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_mma_prep_weights_kernel(const float* __restrict__ W, int K, int C, int N,
                                                                      int w_transposed, float* __restrict__ Wf) {
-  const int J = C / 8, NT = N / 8;
-  const int64_t total = (int64_t)K * J * NT * 32;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int lane = (int)(e & 31);
-    int64_t r = e >> 5;
-    const int n = (int)(r % NT);
-    r /= NT;
-    const int j = (int)(r % J);
-    const int k = (int)(r / J);
-    const int g = lane >> 2, t = lane & 3;
-    const int co = 16 * (n >> 1) + 4 * (g >> 1) + 2 * (n & 1) + (g & 1);
-    float v[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {   // position p = t + 4 h
-      const int ci = 16 * (j >> 1) + 4 * t + 2 * (j & 1) + h;
-      // !w_transposed: W stored [K][C][N];  w_transposed: W stored [K][N][C]
-      v[h] = w_transposed ? W[((int64_t)k * N + co) * C + ci] : W[((int64_t)k * C + ci) * N + co];
-    }
-    const uint32_t h0 = tf32_rn_bits(v[0]), h1 = tf32_rn_bits(v[1]);
-    const uint32_t l0 = __float_as_uint(v[0] - __uint_as_float(h0)), l1 = __float_as_uint(v[1] - __uint_as_float(h1));
-    // (b0_hi, b1_hi) tf32 for the main MMA; bf16 pairs (hi, hi) and (lo, lo) = B fragment of the correction MMA
-    ((float4*)Wf)[e] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(pack_bf16(h0, h1)),
-                                   __uint_as_float(pack_bf16(l0, l1)));
+  const int64_t total = (int64_t)K * (C / 8) * (N / 8) * 32;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    ((float4*)Wf)[e] = prep_mma_frag(W, K, C, N, w_transposed, e);
+}
+
+// All weight re-arrangements of a pass in ONE launch: blockIdx.y = descriptor (8 x int64: W, dst, K, C, N,
+// w_transposed, layout (0 = tcgen05, 1 = mma fragments), unused)
+__global__ void __launch_bounds__(256) conv_prep_batch_kernel(const int64_t* __restrict__ desc) {
+  const int64_t* d = desc + 8 * (int64_t)blockIdx.y;
+  const float* W = (const float*)d[0];
+  float* dst = (float*)d[1];
+  const int K = (int)d[2], C = (int)d[3], N = (int)d[4], wt = (int)d[5], layout = (int)d[6];
+  if (layout == 0) {
+    const int64_t total = (int64_t)K * C * N;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+      dst[e] = prep_tc_elem(W, K, C, N, wt, e);
+  } else {
+    const int64_t total = (int64_t)K * (C / 8) * (N / 8) * 32;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+      ((float4*)dst)[e] = prep_mma_frag(W, K, C, N, wt, e);
   }
 }
 
@@ -603,7 +601,8 @@ int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, const i
   const int64_t total = (int64_t)K * (c_in / 8) * (c_out / 8) * 32;
   int pg = (int)((total + 255) / 256);
   if (pg > kNumSM * 8) pg = kNumSM * 8;
-  conv_mma_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wf);
+  if (W != nullptr)   // W == NULL: scratch already holds the arranged weights (pgs_conv_prep_weights_batch)
+    conv_mma_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wf);
   int rc = PGS_ERR_INVALID;
 #define PGS_MMA_CASE(CI, CO)                                                                   \
   case CI * 1000 + CO:                                                                         \
@@ -621,7 +620,7 @@ int pgs_conv_fwd_mma(const float* X, const float* W, const int32_t* nbr, const i
   }
 #undef PGS_MMA_CASE
   if (rc != PGS_OK) return rc;
-  count_launch(2);
+  count_launch(W != nullptr ? 2 : 1);
   PGS_CHECK_LAUNCH();
   return PGS_OK;
 }
@@ -646,7 +645,8 @@ int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, c
   const int64_t total = (int64_t)K * (c_in / 8) * (c_out / 8) * 32;
   int pg = (int)((total + 255) / 256);
   if (pg > kNumSM * 8) pg = kNumSM * 8;
-  conv_mma_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wf);
+  if (W != nullptr)   // W == NULL: scratch already holds the arranged weights (pgs_conv_prep_weights_batch)
+    conv_mma_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wf);
   const int mtiles = (int)((n_q + 15) / 16);
   const int64_t base = (int64_t)mtiles * (c_out / 16);
   static int target = -1;
@@ -664,7 +664,18 @@ int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, c
   const unsigned gx = (unsigned)((items + kSplitWarps - 1) / kSplitWarps);
   conv_mma_split_kernel<<<gx, kSplitWarps * 32, 0, s>>>(X, (const float4*)Wf, nbr, n_q, K, c_in, c_out, mirror, ksplit,
                                                         mtiles, order, Y);
-  count_launch(2);
+  count_launch(W != nullptr ? 2 : 1);
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+int pgs_conv_prep_weights_batch(const int64_t* desc, int32_t n_desc, int64_t max_elems, void* stream) {
+  if (n_desc <= 0) return PGS_OK;
+  PGS_CHECK_ARG(desc != nullptr && max_elems > 0, "bad descriptor table");
+  int gx = (int)((max_elems + 255) / 256);
+  if (gx > 64) gx = 64;
+  conv_prep_batch_kernel<<<dim3(gx, n_desc), 256, 0, (cudaStream_t)stream>>>(desc);
+  count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;
 }

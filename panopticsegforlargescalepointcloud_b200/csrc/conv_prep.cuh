@@ -1,0 +1,59 @@
+// Weight re-arrangement shared by the conv kernels and the batched prep entry point.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pgs {
+
+constexpr int kPrepKC = 16;   // == kTcKC (conv_tc.cu): input channels per tcgen05 pipeline step
+
+// tcgen05 layout:  Wp[k][j][q][n][4] = B_k[n][j*16 + q*4 .. +3]; e enumerates the OUTPUT floats
+__device__ __forceinline__ float prep_tc_elem(const float* __restrict__ W, int K, int C, int N, int w_transposed, int64_t e) {
+  const int t = (int)(e & 3);
+  int64_t r = e >> 2;
+  const int n = (int)(r % N);
+  r /= N;
+  const int q = (int)(r & 3);
+  r >>= 2;
+  const int J = C / kPrepKC;
+  const int j = (int)(r % J);
+  const int k = (int)(r / J);
+  const int c = j * kPrepKC + q * 4 + t;
+  // !w_transposed: W stored [K][C][N];  w_transposed: W stored [K][N][C]
+  return w_transposed ? W[((int64_t)k * N + n) * C + c] : W[((int64_t)k * C + c) * N + n];
+}
+
+__device__ __forceinline__ uint32_t prep_tf32_rn(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+}
+__device__ __forceinline__ uint32_t prep_pack_bf16(uint32_t first_bits, uint32_t second_bits) {   // first -> low half
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(second_bits)), "f"(__uint_as_float(first_bits)));
+  return d;
+}
+// mma.sync fragment layout (conv_mma.cu): e enumerates float4 fragments [k][j][n][lane]
+__device__ __forceinline__ float4 prep_mma_frag(const float* __restrict__ W, int K, int C, int N, int w_transposed, int64_t e) {
+  const int J = C / 8, NT = N / 8;
+  const int lane = (int)(e & 31);
+  int64_t r = e >> 5;
+  const int n = (int)(r % NT);
+  r /= NT;
+  const int j = (int)(r % J);
+  const int k = (int)(r / J);
+  const int g = lane >> 2, t = lane & 3;
+  const int co = 16 * (n >> 1) + 4 * (g >> 1) + 2 * (n & 1) + (g & 1);
+  float v[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {   // position p = t + 4 h
+    const int ci = 16 * (j >> 1) + 4 * t + 2 * (j & 1) + h;
+    v[h] = w_transposed ? W[((int64_t)k * N + co) * C + ci] : W[((int64_t)k * C + ci) * N + co];
+  }
+  const uint32_t h0 = prep_tf32_rn(v[0]), h1 = prep_tf32_rn(v[1]);
+  const uint32_t l0 = __float_as_uint(v[0] - __uint_as_float(h0)), l1 = __float_as_uint(v[1] - __uint_as_float(h1));
+  // (b0_hi, b1_hi) tf32 for the main MMA; bf16 pairs (hi, hi) and (lo, lo) = B fragment of the correction MMA
+  return make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(prep_pack_bf16(h0, h1)),
+                     __uint_as_float(prep_pack_bf16(l0, l1)));
+}
+
+}  // namespace pgs

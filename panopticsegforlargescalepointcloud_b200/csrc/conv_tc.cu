@@ -25,12 +25,14 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "conv_prep.cuh"
 
 namespace pgs {
 
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;   // rows per CTA == UMMA M
 constexpr int kTcKC = 16;   // input channels per pipeline step (two K=8 tf32 MMAs)
+static_assert(kTcKC == kPrepKC, "conv_prep.cuh must use the same chunk size");
 constexpr int kTcStages = 2;
 
 // ---------------------------------------------------------------------------------------------
@@ -134,24 +136,9 @@ __global__ void __launch_bounds__(256) conv_tc_prep_weights_kernel(const float* 
                                                                     int c_out, int w_transposed,
                                                                     float* __restrict__ Wp) {
   // kernel-side naming: contraction length C (= c_in of the launch), N output channels (= c_out of the launch)
-  const int C = c_in, N = c_out;
-  const int64_t total = (int64_t)K * C * N;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    // e enumerates the OUTPUT layout: ((((k * J + j) * 4 + q) * N + n) * 4 + t)
-    const int t = (int)(e & 3);
-    int64_t r = e >> 2;
-    const int n = (int)(r % N);
-    r /= N;
-    const int q = (int)(r & 3);
-    r >>= 2;
-    const int J = C / kTcKC;
-    const int j = (int)(r % J);
-    const int k = (int)(r / J);
-    const int c = j * kTcKC + q * 4 + t;
-    // !w_transposed: W stored [K][C][N];  w_transposed: W stored [K][N][C]
-    const float v = w_transposed ? W[((int64_t)k * N + n) * C + c] : W[((int64_t)k * C + c) * N + n];
-    Wp[e] = v;
-  }
+  const int64_t total = (int64_t)K * c_in * c_out;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    Wp[e] = prep_tc_elem(W, K, c_in, c_out, w_transposed, e);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -661,7 +648,8 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const in
   const int64_t total = (int64_t)K * c_in * c_out;
   int pg = (int)((total + 255) / 256);
   if (pg > kNumSM * 8) pg = kNumSM * 8;
-  conv_tc_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wp);
+  if (W != nullptr)   // W == NULL: scratch already holds the arranged weights (pgs_conv_prep_weights_batch)
+    conv_tc_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wp);
   const size_t smem = (size_t)kTcStages * (2 * kTcM * kTcKC * 4 + 2 * (size_t)c_out * kTcKC * 4);
   const unsigned gx = (unsigned)((n_q + kTcM - 1) / kTcM);
   static int mode_ts = -1;
@@ -714,7 +702,7 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const in
     else
       conv_tc_kernel<3><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
   }
-  count_launch(2);
+  count_launch(W != nullptr ? 2 : 1);
   PGS_CHECK_LAUNCH();
   return PGS_OK;
 }

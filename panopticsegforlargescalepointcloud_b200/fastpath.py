@@ -71,6 +71,9 @@ class Program:
             if b >= 0:
                 self.consumers[b] += 1
         self.scratch = None
+        self.wprep = None        # arranged weights: per conv a forward and a backward slot
+        self.wprep_off = None
+        self.desc_cache = {}     # (kernel kinds, weight pointers, backward needed) -> device descriptor table
 
     def out_tensor_stride(self, ts0):
         ts = {0: ts0}
@@ -148,7 +151,6 @@ class _UNetFn(torch.autograd.Function):
         n[0], C[0], ts[0] = X.shape[0], X.shape[1], ts0
         # ---- pass 1: shapes, coordinate / kernel maps (the only data-dependent part) ----
         cinfo = [None] * len(prog.convs)
-        scratch_bytes = 0
         for kind, a, b, dst, idx, relu in prog.ops:
             if kind == OP_CONV:
                 mod = prog.convs[idx]
@@ -156,10 +158,10 @@ class _UNetFn(torch.autograd.Function):
                     raise ValueError("expected %d input channels, got %d" % (mod.in_channels, C[a]))
                 km_f, km_b, mf, mb, ts_out, n_out = mod.maps_for(cm, ts[a], n[a])
                 K = mod.kernel_size ** 3
-                cinfo[idx] = (km_f, km_b, mf, mb, K)
+                kind_f = ME._conv_kernel_choice(lib, K, mod.in_channels, mod.out_channels, n_out, km_f is not None)
+                kind_b = ME._conv_kernel_choice(lib, K, mod.out_channels, mod.in_channels, n[a], km_b is not None)
+                cinfo[idx] = (km_f, km_b, mf, mb, K, kind_f, kind_b)
                 n[dst], C[dst], ts[dst] = n_out, mod.out_channels, ts_out
-                scratch_bytes = max(scratch_bytes, ME._conv_scratch_bytes(lib, K, mod.in_channels, mod.out_channels),
-                                    ME._conv_scratch_bytes(lib, K, mod.out_channels, mod.in_channels))
             elif kind == OP_BN:
                 if prog.bns[idx].bn.momentum is None:
                     raise Unsupported("cumulative-average batch norm")
@@ -189,19 +191,51 @@ class _UNetFn(torch.autograd.Function):
         stats = torch.empty(soff[nbn], dtype=torch.float32, device=dev)
         sums = torch.zeros(soff[nbn], dtype=torch.float64, device=dev)
         stats_p, sums_p = stats.data_ptr(), sums.data_ptr()
-        if prog.scratch is None or prog.scratch.numel() < scratch_bytes or prog.scratch.device != dev:
-            prog.scratch = torch.empty(max(scratch_bytes, 1), dtype=torch.uint8, device=dev)
-        scratch_p, scratch_n = prog.scratch.data_ptr(), prog.scratch.numel()
         nconv = len(prog.convs)
+        # ---- arranged weights: forward and backward layout of every convolution in ONE launch ----
+        if prog.wprep is None or prog.wprep.device != dev:
+            offs, tot = [], 0
+            for mod in prog.convs:
+                sz = (mod.kernel_size ** 3 * mod.in_channels * mod.out_channels * 8 + 255) // 256 * 256
+                offs.append((tot, tot + sz, sz))
+                tot += 2 * sz
+            prog.wprep = torch.empty(max(tot, 1), dtype=torch.uint8, device=dev)
+            prog.wprep_off = offs
+            prog.desc_cache = {}
+        need_bwd = any(ctx.needs_input_grad)
+        key = (tuple((c[5], c[6]) for c in cinfo), tuple(p.data_ptr() for p in params[:nconv]), need_bwd)
+        ent = prog.desc_cache.get(key)
+        if ent is None:
+            wbase = prog.wprep.data_ptr()
+            rows, mx = [], 1
+            for i, mod in enumerate(prog.convs):
+                K, kf, kb = cinfo[i][4], cinfo[i][5], cinfo[i][6]
+                of, ob, _ = prog.wprep_off[i]
+                wp = params[i].data_ptr()
+                if kf != "ffma":
+                    rows.append([wp, wbase + of, K, mod.in_channels, mod.out_channels, 0, 0 if kf == "tc" else 1, 0])
+                if need_bwd and kb != "ffma":
+                    rows.append([wp, wbase + ob, K, mod.out_channels, mod.in_channels, 1, 0 if kb == "tc" else 1, 0])
+                mx = max(mx, K * mod.in_channels * mod.out_channels)
+            if len(prog.desc_cache) > 16:
+                prog.desc_cache.clear()
+            ent = (torch.tensor(rows, dtype=torch.int64).to(dev) if rows else None, len(rows), mx)
+            prog.desc_cache[key] = ent
+        if ent[1]:
+            rc = lib.pgs_conv_prep_weights_batch(ent[0].data_ptr(), ent[1], ent[2], sp)
+            if rc:
+                check(rc)
+        wbase = prog.wprep.data_ptr()
         training = [False] * nbn
         tracked = []
         # ---- pass 2: launches ----
         for kind, a, b, dst, idx, relu in prog.ops:
             if kind == OP_CONV:
                 mod = prog.convs[idx]
-                km_f, km_b, mf, mb, K = cinfo[idx]
+                km_f, km_b, mf, mb, K, kind_f, kind_b = cinfo[idx]
+                of, ob, sz = prog.wprep_off[idx]
                 ME._conv_launch(lib, ptrs[a], n[a], params[idx].data_ptr(), K, mod.in_channels, mod.out_channels, km_f,
-                                n[dst], mf, False, ptrs[dst], scratch_p, scratch_n, sp)
+                                n[dst], mf, False, ptrs[dst], wbase + of, sz, sp, kind=kind_f, prepped=True)
             elif kind == OP_BN:
                 bn = prog.bns[idx].bn
                 tr = bool(bn.training)
@@ -258,7 +292,7 @@ class _UNetFn(torch.autograd.Function):
         gbase, gused = garena.data_ptr(), 0
         sums = torch.zeros(soff[nbn], dtype=torch.float64, device=dev)
         sums_p, stats_p = sums.data_ptr(), stats.data_ptr()
-        scratch_p, scratch_n = prog.scratch.data_ptr(), prog.scratch.numel()
+        wbase = prog.wprep.data_ptr()
         # parameter gradients: straight into param.grad where it exists (accumulate), else into one zeroed buffer
         P = prog.params
         needs = ctx.needs_input_grad[4:]
@@ -291,13 +325,15 @@ class _UNetFn(torch.autograd.Function):
                 g = buf
             if kind == OP_CONV:
                 mod = prog.convs[idx]
-                km_f, km_b, mf, mb, K = cinfo[idx]
+                km_f, km_b, mf, mb, K, kind_f, kind_b = cinfo[idx]
                 cin, cout = mod.in_channels, mod.out_channels
                 wp = params[idx].data_ptr()
                 if a != 0 or need_x:
                     dx = gbase + 4 * gused
                     gused += n[a] * C[a]
-                    ME._conv_launch(lib, g, n[dst], wp, K, cout, cin, km_b, n[a], mb, True, dx, scratch_p, scratch_n, sp)
+                    of, ob, sz = prog.wprep_off[idx]
+                    ME._conv_launch(lib, g, n[dst], wp, K, cout, cin, km_b, n[a], mb, True, dx, wbase + ob, sz, sp,
+                                    kind=kind_b, prepped=True)
                     glist[a].append(dx)
                 dw = pgrad(idx)
                 if dw is not None:

@@ -337,11 +337,16 @@ def _conv_scratch_bytes(lib, K, c_in, c_out):
     return nb
 
 
-def _conv_launch(lib, Xp, n_in, Wp, K, c_in, c_out, km, n_q, mirror, w_transposed, Yp, scratch_p, scratch_bytes, sp):
-    """Pick the kernel for this shape and launch it on raw device pointers (ints); returns the kernel kind.
-    km: KernelMap, raw table tensor or None (K == 1 identity)."""
+def _conv_launch(lib, Xp, n_in, Wp, K, c_in, c_out, km, n_q, mirror, w_transposed, Yp, scratch_p, scratch_bytes, sp,
+                 kind=None, prepped=False):
+    """Pick the kernel for this shape (or take `kind`) and launch it on raw device pointers (ints); returns the
+    kernel kind.  km: KernelMap, raw table tensor or None (K == 1 identity).  prepped: `scratch_p` already holds the
+    arranged weights (pgs_conv_prep_weights_batch), so the tensor-core entry points get W == NULL."""
     nbr = km.nbr if isinstance(km, KernelMap) else km
-    kind = _conv_kernel_choice(lib, K, c_in, c_out, n_q, nbr is not None)
+    if kind is None:
+        kind = _conv_kernel_choice(lib, K, c_in, c_out, n_q, nbr is not None)
+    if prepped and kind != "ffma":
+        Wp = None
     nbr_p = order_p = None
     if nbr is not None:
         if kind != "ffma" and SORT_TABLES and isinstance(km, KernelMap) and n_q >= SORT_MIN_ROWS:
