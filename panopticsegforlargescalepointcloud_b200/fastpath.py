@@ -17,6 +17,7 @@ module path stays as the reference implementation of this file (tests/test_gpu_f
 input / parameter gradients and BN running statistics) and is used whenever the module tree is not the plain
 ResNetDown / ResNetUp / ResBlock structure (`Unsupported`).  PGS_FASTPATH=0 disables it.
 """
+import contextlib
 import os
 
 import torch
@@ -26,6 +27,20 @@ from . import me as ME
 from ._lib import check
 
 ENABLED = os.environ.get("PGS_FASTPATH", "1") == "1"
+# weight-gradient kernels on a second stream: they depend only on a layer's input activations and output gradient, not on
+# the input-gradient chain, and the small / mid-size layers of that chain leave most SMs idle
+DW_SIDE_STREAM = os.environ.get("PGS_DW_SIDE_STREAM", "1") == "1"
+# kernel maps / sorted tables / pair lists of the deeper levels built on the second stream while the first layers run:
+# measured no gain (24.9 vs 24.6 ms per step) because the forward pass is bound by the host's launch rate, so it is off
+MAPS_SIDE_STREAM = os.environ.get("PGS_MAPS_SIDE_STREAM", "0") == "1"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    s = _SIDE.get(dev.index)
+    if s is None:
+        s = _SIDE[dev.index] = torch.cuda.Stream(device=dev)
+    return s
 
 OP_CONV, OP_BN, OP_ADD, OP_CAT = 0, 1, 2, 3
 BN_ACC, BN_ZEROED = 1, 2   # include/pgs_b200.h: PGS_BN_ACCUMULATE_PARAM_GRADS, PGS_BN_SUMS_ZEROED
@@ -150,30 +165,67 @@ class _UNetFn(torch.autograd.Function):
         n, C, ts = [0] * S, [0] * S, [0] * S
         n[0], C[0], ts[0] = X.shape[0], X.shape[1], ts0
         # ---- pass 1: shapes, coordinate / kernel maps (the only data-dependent part) ----
+        # The strided coordinate maps (whose sizes the host must read back) are built first on the main stream; the
+        # kernel maps, their occupancy-sorted copies and the pair lists of the weight gradient then go to a second
+        # stream in order of first use, so that the tables of the deeper levels are built while the first layers
+        # already run (each convolution waits for the event of its own tables).
+        need_bwd = any(ctx.needs_input_grad)
+        maps_side = MAPS_SIDE_STREAM
+        if maps_side:
+            t = {0: ts0}
+            for kind, a, b, dst, idx, relu in prog.ops:
+                t[dst] = t[a]
+                if kind == OP_CONV:
+                    mod = prog.convs[idx]
+                    if mod.stride > 1:
+                        if mod.TRANSPOSE:
+                            t[dst] = t[a] // mod.stride
+                        else:
+                            t[dst] = t[a] * mod.stride
+                            cm.stride(t[a], t[dst])
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(main)   # the coordinate maps; and everything the previous step still reads from old tables
         cinfo = [None] * len(prog.convs)
-        for kind, a, b, dst, idx, relu in prog.ops:
-            if kind == OP_CONV:
-                mod = prog.convs[idx]
-                if C[a] != mod.in_channels:
-                    raise ValueError("expected %d input channels, got %d" % (mod.in_channels, C[a]))
-                km_f, km_b, mf, mb, ts_out, n_out = mod.maps_for(cm, ts[a], n[a])
-                K = mod.kernel_size ** 3
-                kind_f = ME._conv_kernel_choice(lib, K, mod.in_channels, mod.out_channels, n_out, km_f is not None)
-                kind_b = ME._conv_kernel_choice(lib, K, mod.out_channels, mod.in_channels, n[a], km_b is not None)
-                cinfo[idx] = (km_f, km_b, mf, mb, K, kind_f, kind_b)
-                n[dst], C[dst], ts[dst] = n_out, mod.out_channels, ts_out
-            elif kind == OP_BN:
-                if prog.bns[idx].bn.momentum is None:
-                    raise Unsupported("cumulative-average batch norm")
-                n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
-            elif kind == OP_ADD:
-                if (n[a], C[a], ts[a]) != (n[b], C[b], ts[b]):
-                    raise ValueError("sum of sparse tensors on different maps")
-                n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
-            else:
-                if (n[a], ts[a]) != (n[b], ts[b]):
-                    raise ValueError("concatenation of sparse tensors on different maps")
-                n[dst], C[dst], ts[dst] = n[a], C[a] + C[b], ts[a]
+        cevent = [None] * len(prog.convs)
+        with (torch.cuda.stream(side) if maps_side else contextlib.nullcontext()):
+            for kind, a, b, dst, idx, relu in prog.ops:
+                if kind == OP_CONV:
+                    mod = prog.convs[idx]
+                    if C[a] != mod.in_channels:
+                        raise ValueError("expected %d input channels, got %d" % (mod.in_channels, C[a]))
+                    K = mod.kernel_size ** 3
+                    before = len(cm.kmaps)
+                    km_f, km_b, mf, mb, ts_out, n_out = mod.maps_for(cm, ts[a], n[a])
+                    kind_f = ME._conv_kernel_choice(lib, K, mod.in_channels, mod.out_channels, n_out, km_f is not None)
+                    kind_b = ME._conv_kernel_choice(lib, K, mod.out_channels, mod.in_channels, n[a], km_b is not None)
+                    if maps_side and km_f is not None:
+                        fresh = len(cm.kmaps) != before
+                        for km, kd, nq in ((km_f, kind_f, n_out), (km_b, kind_b, n[a])):
+                            if (kd != "ffma" and ME.SORT_TABLES and nq >= ME.SORT_MIN_ROWS and km._sorted is None
+                                    and (km is km_f or need_bwd)):
+                                km.sorted()
+                                fresh = True
+                        if need_bwd and km_f._pairs is None:
+                            km_f.pairs()
+                            fresh = True
+                        if fresh:
+                            cevent[idx] = torch.cuda.Event()
+                            cevent[idx].record(side)
+                    cinfo[idx] = (km_f, km_b, mf, mb, K, kind_f, kind_b)
+                    n[dst], C[dst], ts[dst] = n_out, mod.out_channels, ts_out
+                elif kind == OP_BN:
+                    if prog.bns[idx].bn.momentum is None:
+                        raise Unsupported("cumulative-average batch norm")
+                    n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
+                elif kind == OP_ADD:
+                    if (n[a], C[a], ts[a]) != (n[b], C[b], ts[b]):
+                        raise ValueError("sum of sparse tensors on different maps")
+                    n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
+                else:
+                    if (n[a], ts[a]) != (n[b], ts[b]):
+                        raise ValueError("concatenation of sparse tensors on different maps")
+                    n[dst], C[dst], ts[dst] = n[a], C[a] + C[b], ts[a]
         if min(n) <= 0:
             raise Unsupported("empty level")
         # ---- arenas ----
@@ -202,7 +254,6 @@ class _UNetFn(torch.autograd.Function):
             prog.wprep = torch.empty(max(tot, 1), dtype=torch.uint8, device=dev)
             prog.wprep_off = offs
             prog.desc_cache = {}
-        need_bwd = any(ctx.needs_input_grad)
         key = (tuple((c[5], c[6]) for c in cinfo), tuple(p.data_ptr() for p in params[:nconv]), need_bwd)
         ent = prog.desc_cache.get(key)
         if ent is None:
@@ -234,6 +285,8 @@ class _UNetFn(torch.autograd.Function):
                 mod = prog.convs[idx]
                 km_f, km_b, mf, mb, K, kind_f, kind_b = cinfo[idx]
                 of, ob, sz = prog.wprep_off[idx]
+                if cevent[idx] is not None:
+                    main.wait_event(cevent[idx])   # this conv's tables were built on the side stream
                 ME._conv_launch(lib, ptrs[a], n[a], params[idx].data_ptr(), K, mod.in_channels, mod.out_channels, km_f,
                                 n[dst], mf, False, ptrs[dst], wbase + of, sz, sp, kind=kind_f, prepped=True)
             elif kind == OP_BN:
@@ -309,6 +362,12 @@ class _UNetFn(torch.autograd.Function):
                 return None
             return P[i].grad.data_ptr() if direct[i] else gflat_p + 4 * goff[i]
 
+        side = sp_side = None
+        if DW_SIDE_STREAM:
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(main)          # activations, zeroed gradient buffers, dOut
+            sp_side = _lib.c_void_p(side.cuda_stream)
         glist = [[] for _ in range(prog.n_slots)]
         glist[prog.out_slot].append(dOut.data_ptr())
         for kind, a, b, dst, idx, relu in reversed(prog.ops):
@@ -337,12 +396,19 @@ class _UNetFn(torch.autograd.Function):
                     glist[a].append(dx)
                 dw = pgrad(idx)
                 if dw is not None:
-                    if km_f is not None:
-                        in_idx, out_idx, offs, max_pairs = km_f.pairs()
+                    spw = sp
+                    pl = km_f.pairs() if km_f is not None else None   # (built on the main stream on first use)
+                    if side is not None:        # g and the pair lists are complete on the main stream here
+                        ev = torch.cuda.Event()
+                        ev.record(main)
+                        side.wait_event(ev)
+                        spw = sp_side
+                    if pl is not None:
+                        in_idx, out_idx, offs, max_pairs = pl
                         rc = lib.pgs_conv_bwd_weight(ptrs[a], g, in_idx.data_ptr(), out_idx.data_ptr(), offs.data_ptr(),
-                                                     max_pairs, K, cin, cout, int(mf), dw, sp)
+                                                     max_pairs, K, cin, cout, int(mf), dw, spw)
                     else:
-                        rc = lib.pgs_conv_bwd_weight(ptrs[a], g, None, None, None, n[a], 1, cin, cout, 0, dw, sp)
+                        rc = lib.pgs_conv_bwd_weight(ptrs[a], g, None, None, None, n[a], 1, cin, cout, 0, dw, spw)
                     if rc:
                         check(rc)
             elif kind == OP_BN:
@@ -373,6 +439,8 @@ class _UNetFn(torch.autograd.Function):
                 glist[a].append(ga)
                 glist[b].append(gb)
         assert gused <= total
+        if side is not None:
+            main.wait_stream(side)      # gradients complete (and the arenas reusable) for whatever follows on the main stream
         dX = None
         if need_x:
             g0 = glist[0]
