@@ -214,7 +214,11 @@ class BaseModel(nn.Module):
         params = dict((opt_cfg.get("params", {}) or {})) if hasattr(opt_cfg, "get") else {}
         params.setdefault("lr", 1e-3)
         cls = getattr(torch.optim, (opt_cfg.get("class", "Adam") if hasattr(opt_cfg, "get") else "Adam"))
-        self._optimizer = cls(self.parameters(), **params)
+        plist = list(self.parameters())
+        if (cls in (torch.optim.Adam, torch.optim.AdamW) and "fused" not in params and "foreach" not in params
+                and plist and all(p.is_cuda and p.dtype == torch.float32 for p in plist)):
+            params["fused"] = True   # same update rule in 2-3 multi-tensor kernels instead of ~30 (0.6 ms + 1 ms of host time)
+        self._optimizer = cls(plist, **params)
         self._lr_scheduler = torch.optim.lr_scheduler.ExponentialLR(self._optimizer, gamma=0.9885)
         return self._optimizer
 
