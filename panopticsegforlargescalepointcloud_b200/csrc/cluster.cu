@@ -19,6 +19,8 @@
 // Integer / compare work, L2- and HBM-bound; nothing here is a GEMM.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pgs {
@@ -286,27 +288,28 @@ __global__ void __launch_bounds__(kCT) rg_init_kernel(const int32_t* __restrict_
   if (i < n) label[i] = gid[i] >= 0 ? (int32_t)i : -1;
 }
 
-// 8 lanes per source row (rows hold ~10-30 entries: a whole warp per row left most lanes idle and made the launch
-// 6.4 M threads for 200 k points): push my (freshest) label along my out-edges
-constexpr int kRgLanes = 8;
+// LANES lanes per source row (rows hold ~10-30 entries; a whole warp per row leaves most lanes idle and makes the launch
+// 6.4 M threads for 200 k points): push my (freshest) label along my out-edges.  PGS_RG_LANES selects 8 (default) / 32.
+template <int LANES>
 __global__ void __launch_bounds__(kCT) rg_push_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ cnt,
                                                        const int32_t* __restrict__ gid, int64_t n, int nsample,
                                                        int32_t* __restrict__ label, int32_t* __restrict__ changed) {
-  const int lane = threadIdx.x & (kRgLanes - 1);
-  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kRgLanes;
+  const int lane = threadIdx.x & (LANES - 1);
+  const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   if (q >= n || gid[q] < 0) return;
   const int c = cnt[q];
   const int32_t* row = nbr + q * nsample;
   const int mine = *(volatile int32_t*)&label[q];
   bool any = false;
-  for (int e = lane; e < c; e += kRgLanes) {
+  for (int e = lane; e < c; e += LANES) {
     const int j = row[e];
     if (*(volatile int32_t*)&label[j] > mine) {
       atomicMin(&label[j], mine);
       any = true;
     }
   }
-  if (any) *changed = 1;
+  // one flag for the whole grid: read before write, so that after the first few writers nobody stores any more
+  if (any && *(volatile int32_t*)changed == 0) *changed = 1;
 }
 
 // pointer jumping: label[v] = label[label[v]] until stable (valid because "reaches" is transitive)
@@ -450,9 +453,17 @@ int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid,
   if (n == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   PGS_CUDA(cudaMemsetAsync(changed, 0, sizeof(int32_t), s));
-  const int64_t threads = n * kRgLanes;
+  static int lanes = 0;
+  if (lanes == 0) {
+    const char* e = getenv("PGS_RG_LANES");
+    lanes = (e && atoi(e) == 32) ? 32 : 8;
+  }
+  const int64_t threads = n * lanes;
   for (int r = 0; r < rounds; ++r) {
-    rg_push_kernel<<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, changed);
+    if (lanes == 32)
+      rg_push_kernel<32><<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, changed);
+    else
+      rg_push_kernel<8><<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, changed);
     rg_jump_kernel<<<grid_for_c(n), kCT, 0, s>>>(n, label, changed);
     count_launch(2);
   }
