@@ -85,7 +85,6 @@ class Program:
             self.consumers[a] += 1
             if b >= 0:
                 self.consumers[b] += 1
-        self.scratch = None
         self.wprep = None        # arranged weights: per conv a forward and a backward slot
         self.wprep_off = None
         self.desc_cache = {}     # (kernel kinds, weight pointers, backward needed) -> device descriptor table
