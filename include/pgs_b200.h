@@ -262,6 +262,22 @@ int pgs_bn_backward(const float* X, const float* Y, const float* dY, int64_t n, 
                     const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, double* sums,
                     float* dX, float* dweight, float* dbias, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Flat-kernel mean shift on embeddings  (replaces sklearn.cluster.MeanShift(bandwidth, bin_seeding=True).fit as called
+ *                                        by torch_points3d/utils/meanshift_cluster.py:9-18,72-123; call sites
+ *                                        models/panoptic/PointGroup3heads.py:235,276,323,376, pointgroupembed.py:491,532)
+ *   pgs_ms_iterate : every seed climbs to its mode (mean of the points within `bandwidth`, until it moves less than
+ *                    1e-3 * bandwidth or max_iter); centers fp32 [n_seeds, D], counts = points within the bandwidth at the
+ *                    last query (0: nothing near the seed, drop it), iters = completed iterations
+ *   pgs_ms_assign  : label = index of the nearest centre (fp64 distances, ties to the lower index); dist nullable
+ * D in 1..8.  Seeding (grid bins), the greedy removal of near-duplicate centres and the label order live in
+ * meanshift.py (a few thousand centres: host work, like the reference).
+ * ------------------------------------------------------------------------------------------ */
+int pgs_ms_iterate(const float* X, int64_t n, int32_t D, const float* seeds, int64_t n_seeds, float bandwidth,
+                   int32_t max_iter, float* centers, int32_t* counts, int32_t* iters, void* stream);
+int pgs_ms_assign(const float* X, int64_t n, int32_t D, const float* centers, int32_t n_centers, int32_t* labels,
+                  double* dist, void* stream);
+
 /* flags of the _ex variants (used by the fused U-Net executor, fastpath.py) */
 #define PGS_BN_ACCUMULATE_PARAM_GRADS 1 /* dweight / dbias += instead of = (write straight into param.grad) */
 #define PGS_BN_SUMS_ZEROED 2            /* the caller zeroed `sums` (one memset for all layers of a pass) */

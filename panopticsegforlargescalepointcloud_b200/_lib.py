@@ -45,6 +45,9 @@ SIGNATURES = {
     "pgs_hdb_mst": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_size_t, c_void_p]),
     "pgs_hdb_labels_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p, c_void_p]),
+    "pgs_ms_iterate": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_float, c_int32, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "pgs_ms_assign": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgs_conv_tc_supported": (c_int, [c_int32, c_int32]),
     "pgs_conv_tc_scratch_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "pgs_conv_fwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32,

@@ -17,7 +17,8 @@ OmegaConf in the reference).
 Differences by design (DESIGN.md "host path"): the batch lives on the device for the whole step (the
 reference keeps it on the CPU and bounces proposals through host memory, PointGroup3heads.py:97,416),
 proposals are gathered with one index op instead of a python loop, and there is no multiprocessing.Pool.
-cluster_type values that need MeanShift (3-6 of PointGroup3heads) are SURVEY 8f #1 ("next") and raise.
+cluster_type values with MeanShift on the embeddings (3-6 of PointGroup3heads, 7-8 of PointGroupEmbed: paper settings I,
+IV, V) run on meanshift.py; the random feature-subset loops (`cluster_loop*`) are not reproduced.
 """
 from collections import OrderedDict
 from typing import List, NamedTuple
@@ -26,6 +27,7 @@ import torch
 import torch.nn as nn
 
 from . import hdbscan as _hdbscan
+from . import meanshift as _meanshift
 from . import losses as L
 from . import tpk
 from . import me as _me
@@ -309,6 +311,32 @@ class _PanopticBase(BaseModel):
         label_batch = self.input.batch[mask]
         return _hdbscan.cluster_single(feats[mask].detach(), torch.unique(label_batch), label_batch, local_ind, ctype)
 
+    def _meanshift(self, feats, predicted_labels, ctype):
+        """Embedding branch of the reference's _cluster3.._cluster6 / pointgroupembed._cluster7/8: thing points only,
+        per scene, sklearn-equivalent mean shift with opt.bandwidth (meanshift_cluster.cluster_single)."""
+        mask = self._thing_mask(predicted_labels)
+        local_ind = torch.nonzero(mask).squeeze(1)
+        label_batch = self.input.batch[mask]
+        bw = self.opt.bandwidth if self.opt.bandwidth is not None else 0.6
+        return _meanshift.cluster_single(feats[mask].detach(), torch.unique(label_batch), label_batch, local_ind, ctype, bw)
+
+    def _cluster_ms(self, semantic_logits, offset_logits, embed_logits, raw, votes, ms_type):
+        """region_grow on raw positions (nsample default) and / or shifted positions (nsample 200), plus mean shift on
+        the embeddings: PointGroup3heads._cluster3 (-,-), _cluster4 (raw), _cluster5 (votes), _cluster6 (raw + votes);
+        pointgroupembed._cluster7 (-,-), _cluster8 (raw)."""
+        pred = torch.max(semantic_logits, 1)[1]
+        clusters, types = [], []
+        if raw:
+            c = self._region_grow(self.raw_pos, pred)
+            clusters += c
+            types += [0] * len(c)
+        if votes:
+            c = self._region_grow(self.raw_pos + offset_logits.detach(), pred, nsample=200)
+            types += [1 if raw else 0] * len(c)
+            clusters += c
+        c, t = self._meanshift(embed_logits, pred, ms_type)
+        return clusters + c, torch.tensor(types + t, dtype=torch.uint8, device=self.device)
+
     def _cluster_votes(self, semantic_logits, offset_logits):                      # PointGroup3heads._cluster
         pred = torch.max(semantic_logits, 1)[1]
         clusters = self._region_grow(self.raw_pos + offset_logits.detach(), pred, nsample=200)
@@ -421,9 +449,17 @@ class PointGroup3heads(_PanopticBase):
             return self._cluster_votes(sem, off)
         if ct == 2:
             return self._cluster_pos_and_votes(sem, off)
+        if ct == 3:
+            return self._cluster_ms(sem, off, emb, False, False, 0)   # PointGroup3heads._cluster3
+        if ct == 4:
+            return self._cluster_ms(sem, off, emb, True, False, 1)    # _cluster4
+        if ct == 5:
+            return self._cluster_ms(sem, off, emb, False, True, 1)    # _cluster5 (paper setting IV)
+        if ct == 6:
+            return self._cluster_ms(sem, off, emb, True, True, 2)     # _cluster6 (paper setting V)
         if ct == 14:
             return self._cluster_hdbscan_embed(sem, emb)
-        raise NotImplementedError("cluster_type %r needs MeanShift on embeddings (SURVEY 8f #1, next)" % ct)
+        raise NotImplementedError("cluster_type %r" % ct)
 
 
 class PointGroup(_PanopticBase):
@@ -449,9 +485,13 @@ class PointGroupEmbed(_PanopticBase):
         ct = self.opt.cluster_type
         if ct == 1:
             return self._cluster_hdbscan_xyz_embed(sem, emb)
+        if ct == 7:
+            return self._cluster_ms(sem, off, emb, False, False, 0)   # pointgroupembed._cluster7 (paper setting I)
+        if ct == 8:
+            return self._cluster_ms(sem, off, emb, True, False, 1)    # pointgroupembed._cluster8
         if ct == 14:
             return self._cluster_hdbscan_embed(sem, emb)
-        raise NotImplementedError("cluster_type %r needs MeanShift on embeddings (SURVEY 8f #1, next)" % ct)
+        raise NotImplementedError("cluster_type %r (random feature-subset loops, SURVEY App. E)" % ct)
 
 
 def paper_options(kind="urban", cluster_type=1, grid=0.12, use_score_net=True, prepare_epoch=30, scorer=True,

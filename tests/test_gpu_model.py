@@ -135,3 +135,39 @@ def test_embed_model_hdbscan_path(cuda_device):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+@pytest.mark.parametrize("cls,ct", [("PointGroup3heads", 5), ("PointGroup3heads", 6), ("PointGroupEmbed", 7)])
+def test_meanshift_cluster_types(cuda_device, cls, ct):
+    """Paper settings IV / V / I (PointGroup3heads._cluster5 / _cluster6, pointgroupembed._cluster7): region growing on
+    raw / shifted positions plus mean shift on the embedding head output; the embedding branch equals scikit-learn's
+    MeanShift(bandwidth=0.6, bin_seeding=True) run per scene on the same embeddings, cluster types as the reference
+    numbers them."""
+    from sklearn.cluster import MeanShift
+    panoptic, scenes = _pkg()
+    batch = _make("forest", 2500, 0.2, 4.0, 2, seed0=3)
+    torch.manual_seed(2022)
+    opt = panoptic.paper_options("forest", cluster_type=ct, grid=0.2, use_score_net=False, scorer=False, backbone="two_level")
+    model = getattr(panoptic, cls)(opt, "dummy", panoptic.DatasetProperties("forest"), None).to(cuda_device)
+    model.eval()
+    model.set_input(batch, cuda_device)
+    out = model.forward(epoch=1)
+    emb = out.embed_logits.detach().cpu().numpy()
+    pred = out.semantic_logits.argmax(1).cpu().numpy()
+    mask = ~np.isin(pred, [-1] + list(scenes.stuff_classes("forest")))
+    local = np.nonzero(mask)[0]
+    lb = np.asarray(batch.batch)[mask]
+    want = []
+    for s in np.unique(lb):
+        m = lb == s
+        if m.sum() > 3:
+            lab = MeanShift(bandwidth=0.6, bin_seeding=True).fit(emb[mask][m]).labels_
+            want += [local[m][lab == l] for l in np.unique(lab)]
+    types = out.cluster_type.cpu().numpy()
+    ms_type = {5: 1, 6: 2, 7: 0}[ct]
+    n_rg = len(out.clusters) - len(want)
+    assert n_rg >= 0 and np.all(types[n_rg:] == ms_type)
+    if ct == 6:
+        assert set(types[:n_rg].tolist()) <= {0, 1}
+    for a, b in zip(out.clusters[n_rg:], want):
+        assert np.array_equal(a.cpu().numpy(), b)
