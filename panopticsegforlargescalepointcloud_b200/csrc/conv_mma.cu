@@ -24,7 +24,7 @@
 
 namespace pgs {
 
-constexpr int kMmWarps = 8;
+constexpr int kMmWarps = 4;   // 4-warp CTAs (64 / 128 rows): measured 2-13 % faster than 8 warps (finer barrier domains, better tail balance on the 25-30 k-row levels)
 constexpr int kMmThreads = kMmWarps * 32;
 constexpr int kMmMaxK = 27;
 
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) conv_prep_batch_kernel(const int64_t* __r
 // WS = 0: weights of one kernel offset staged in shared memory (cp.async double buffer, one barrier per offset)
 // WS = 1: weight fragments read straight from global memory (L1-resident for the small shapes), no barrier
 template <int CIN, int COUT, int MT, int WS>
-__global__ void __launch_bounds__(kMmThreads, (CIN * COUT * MT <= 32 * 32 ? 2 : 1)) conv_mma_kernel(const float* __restrict__ X, const float4* __restrict__ Wf,
+__global__ void __launch_bounds__(kMmThreads, (CIN * COUT * MT <= 32 * 32 ? 4 : 2)) conv_mma_kernel(const float* __restrict__ X, const float4* __restrict__ Wf,
                                                                const int32_t* __restrict__ nbr, int64_t n_q, int K,
                                                                int mirror, const int32_t* __restrict__ order,
                                                                float* __restrict__ Y) {
@@ -428,10 +428,10 @@ template <int CIN, int COUT>
 static int launch_mmaq(const float* X, const float* Wf, const int32_t* nbr, const int32_t* order, int64_t n_q, int K,
                        int mirror, float* Y, cudaStream_t s) {
   // ring depth and CTAs per SM from the shared memory of one ring stage (weight fragments + per-thread row pieces)
-  constexpr int STAGE = CIN * COUT * 8 + CIN * 512;
-  constexpr int D = (STAGE <= 12 * 1024) ? 4 : (STAGE <= 30 * 1024 ? 3 : 2);
+  constexpr int STAGE = CIN * COUT * 8 + CIN * 2 * kMmThreads;
+  constexpr int D = (STAGE <= 8 * 1024) ? 4 : (STAGE <= 20 * 1024 ? 3 : 2);
   constexpr int FIT = (224 * 1024) / (kMmMaxK * kMmWarps * 16 * 4 + D * STAGE + 1024);
-  constexpr int RCAP = COUT <= 16 ? 4 : (COUT <= 32 ? 3 : 2);   // 2 * COUT accumulator registers per thread
+  constexpr int RCAP = COUT <= 16 ? 8 : (COUT <= 32 ? 6 : 4);   // 2 * COUT accumulator registers per thread, 128-thread CTAs
   constexpr int MINB = FIT < 1 ? 1 : (FIT > RCAP ? RCAP : FIT);
   constexpr int R = kMmWarps * 16;
   constexpr size_t smem = (size_t)kMmMaxK * R * 4 +
