@@ -60,7 +60,7 @@ cases = [(0, 16, 16), (0, 32, 16), (0, 64, 16), (0, 16, 32), (0, 16, 64), (1, 32
          (2, 48, 48), (2, 32, 48), (2, 48, 32), ("0>1", 16, 16), ("1>0", 64, 64), (1, 64, 64), (0, 48, 48), (1, 48, 64)]
 small = [(3, 64, 64), (3, 160, 64), (4, 80, 80), (4, 192, 80), (5, 96, 96), (5, 192, 192), (6, 112, 112), (2, 48, 48),
          (2, 128, 48), (3, 128, 128)]
-cases = [c + ("mma",) for c in cases] + [c + ("split",) for c in small]
+cases = [c + ("mma",) for c in cases + [(3, 64, 64), (3, 48, 64), (3, 64, 48)]] + [c + ("split",) for c in small]
 if os.environ.get("CASES"):
     want = {tuple(c.split(":")) for c in os.environ["CASES"].split(",")}
     cases = [c for c in cases if (str(c[0]), str(c[1]), str(c[2])) in want]
