@@ -149,3 +149,65 @@ def test_region_grow_full_size_c2(cuda_device):
     assert allm.unique().numel() == allm.numel()
     for c in got:
         assert c.numel() >= 10 and len(set(pred[c.cpu().numpy()])) == 1
+
+
+def test_instance_iou_matches_definition(cuda_device):
+    """tpk.instance_iou (core/losses/panoptic_losses.py:37): IoU of every proposal against every ground-truth instance of
+    ITS scene, columns = instances 1..M_s of scene 0, then of scene 1, ...; other scenes' columns are 0."""
+    from panopticsegforlargescalepointcloud_b200 import tpk
+    rng = np.random.default_rng(4)
+    n_per, M = [900, 1200, 700], [5, 8, 3]
+    batch = np.concatenate([np.full(n, s) for s, n in enumerate(n_per)])
+    inst = np.concatenate([rng.integers(0, m + 1, n) for n, m in zip(n_per, M)])       # 0 = no instance
+    for s, m in enumerate(M):                                                           # every id 1..M_s occurs
+        inst[np.nonzero(batch == s)[0][:m]] = np.arange(1, m + 1)
+    starts = np.concatenate([[0], np.cumsum(n_per)])
+    props = []
+    for s in range(3):
+        for _ in range(6):
+            k = int(rng.integers(5, 200))
+            props.append(np.sort(rng.choice(np.arange(starts[s], starts[s + 1]), k, replace=False)))
+    want = np.zeros((len(props), sum(M)), np.float32)
+    col0 = np.concatenate([[0], np.cumsum(M)])
+    for p, idx in enumerate(props):
+        s = batch[idx[0]]
+        for g in range(1, M[s] + 1):
+            G = np.nonzero((batch == s) & (inst == g))[0]
+            inter = len(np.intersect1d(idx, G))
+            want[p, col0[s] + g - 1] = inter / float(len(idx) + len(G) - inter)
+    got = tpk.instance_iou([torch.from_numpy(p).to(cuda_device) for p in props], torch.from_numpy(inst).to(cuda_device),
+                           torch.from_numpy(batch).to(cuda_device))
+    assert tuple(got.shape) == want.shape and np.allclose(got.cpu().numpy(), want, atol=1e-6)
+
+
+def test_get_instances_matches_reference_nms(cuda_device):
+    """PanopticResults.get_instances (models/panoptic/structure_3heads.py:28-71): dense-mask cross IoU + greedy NMS in
+    descending score order + size / score filters, restated with numpy; the product uses a sparse incidence matrix."""
+    from panopticsegforlargescalepointcloud_b200 import panoptic
+    rng = np.random.default_rng(5)
+    N, n_prop = 6000, 40
+    clusters = []
+    for i in range(n_prop):
+        c0 = int(rng.integers(0, N - 600))
+        clusters.append(np.sort(rng.choice(np.arange(c0, c0 + 600), int(rng.integers(50, 400)), replace=False)))
+    scores = rng.permutation(n_prop).astype(np.float32) / n_prop          # distinct: no tie ambiguity in the argsort
+    masks = np.zeros((n_prop, N), np.float32)
+    for i, c in enumerate(clusters):
+        masks[i, c] = 1
+    inter = masks @ masks.T
+    num = masks.sum(1)
+    cross = inter / (num[:, None] + num[None, :] - inter)
+    ixs = list(np.argsort(scores)[::-1])
+    pick = []
+    while ixs:
+        i = ixs.pop(0)
+        pick.append(i)
+        ixs = [j for j in ixs if not cross[i, j] > 0.3]
+    want = [i for i in pick if len(clusters[i]) > 100 and scores[i] > 0.5]
+    res = panoptic.PanopticResults(semantic_logits=torch.zeros(N, 2, device=cuda_device), offset_logits=None, embed_logits=None,
+                                   cluster_scores=torch.from_numpy(scores).to(cuda_device), mask_scores=None,
+                                   clusters=[torch.from_numpy(c).to(cuda_device) for c in clusters], cluster_type=None)
+    ids, out = res.get_instances(nms_threshold=0.3, min_cluster_points=100, min_score=0.5)
+    assert [int(i) for i in ids] == [int(i) for i in want]
+    for o, i in zip(out, want):
+        assert np.array_equal(o.cpu().numpy(), clusters[i])
