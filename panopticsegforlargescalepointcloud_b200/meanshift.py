@@ -19,6 +19,28 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 
+def select_centres(centres, counts, bandwidth):
+    """Host stage (_mean_shift.py:513-545): converged (centre, points-within-bandwidth) pairs -> cluster centres.
+    Seeds with no point nearby are dropped, the rest sorted by (intensity, centre tuple) descending, and every centre
+    within `bandwidth` of an earlier kept one is removed.  A few thousand rows, strictly sequential, numpy."""
+    keep = counts > 0
+    if not keep.any():
+        raise ValueError("No point was within bandwidth=%f of any seed." % bandwidth)
+    c, k = centres[keep], counts[keep]
+    D = c.shape[1]
+    order = np.lexsort(tuple(c[:, d] for d in range(D - 1, -1, -1)) + (k,))[::-1]
+    c = c[order]
+    c64 = c.astype(np.float64)
+    unique = np.ones(len(c), dtype=bool)
+    h2 = float(bandwidth) * float(bandwidth)
+    for i in range(len(c)):
+        if unique[i]:
+            d2 = ((c64 - c64[i]) ** 2).sum(1)
+            unique[d2 <= h2] = False
+            unique[i] = True
+    return np.ascontiguousarray(c[unique])
+
+
 class MeanShift:
     def __init__(self, *, bandwidth=None, seeds=None, bin_seeding=False, min_bin_freq=1, cluster_all=True, n_jobs=None,
                  max_iter=300, device=None):
@@ -61,25 +83,8 @@ class MeanShift:
         iters = torch.empty(ns, dtype=torch.int32, device=dev)
         check(lib.pgs_ms_iterate(ptr(X), n, D, ptr(seeds), ns, self.bandwidth, self.max_iter, ptr(centers), ptr(counts),
                                  ptr(iters), stream_ptr()))
-        c = centers.cpu().numpy()
-        k = counts.cpu().numpy()
         self.n_iter_ = int(iters.max())
-        keep = k > 0
-        if not keep.any():
-            raise ValueError("No point was within bandwidth=%f of any seed." % self.bandwidth)
-        c, k = c[keep], k[keep]
-        # sorted(center_intensity_dict.items(), key=(intensity, centre tuple), reverse=True)  (_mean_shift.py:523-527)
-        order = np.lexsort(tuple(c[:, d] for d in range(D - 1, -1, -1)) + (k,))[::-1]
-        c, k = c[order], k[order]
-        c64 = c.astype(np.float64)
-        unique = np.ones(len(c), dtype=bool)
-        h2 = self.bandwidth * self.bandwidth
-        for i in range(len(c)):
-            if unique[i]:
-                d2 = ((c64 - c64[i]) ** 2).sum(1)
-                unique[d2 <= h2] = False
-                unique[i] = True
-        cc = np.ascontiguousarray(c[unique])
+        cc = select_centres(centers.cpu().numpy(), counts.cpu().numpy(), self.bandwidth)
         cdev = torch.from_numpy(cc).to(dev)
         labels = torch.empty(n, dtype=torch.int32, device=dev)
         dist = None if self.cluster_all else torch.empty(n, dtype=torch.float64, device=dev)
