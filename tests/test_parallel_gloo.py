@@ -79,3 +79,29 @@ def test_bucket_views_survive_zero_grad():
     assert all(p.grad.data_ptr() >= b.flat.data_ptr() for p in net.parameters())
     assert float(b.flat.abs().sum()) > 0
     assert parallel.shard_scenes(5, 1, 2) == [1, 3]
+
+
+def test_data_parallel_step_hooks_zero_and_reattach():
+    """DataParallelStep installs the flat-buffer zero hook and the post-backward hook on the model; gradients written
+    in place into `param.grad` (what the fused executor's kernels do) land in the flat buffer."""
+    sys.path.insert(0, ROOT)
+    from panopticsegforlargescalepointcloud_b200 import parallel
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = _net()
+            self._grad_hook = None
+
+    m = Model()
+    dp = parallel.DataParallelStep(m, broadcast=False)
+    assert m._grad_hook is not None and m._zero_grad_hook is not None
+    for p in m.parameters():
+        p.grad.add_(1.0)                       # in-place accumulation, like the dW / BN kernels
+    assert float(dp.bucket.flat.sum()) == sum(p.numel() for p in m.parameters())
+    m._zero_grad_hook()
+    assert float(dp.bucket.flat.abs().sum()) == 0.0 and all(float(p.grad.abs().sum()) == 0.0 for p in m.parameters())
+    first = next(m.parameters())
+    first.grad = torch.ones_like(first)        # something replaced a view: the hook copies it back and re-attaches
+    m._grad_hook()
+    assert first.grad.data_ptr() == dp.bucket.views[0].data_ptr() and float(dp.bucket.flat.sum()) == first.numel()
