@@ -298,6 +298,88 @@ int pgs_bn_backward_ex(const float* X, const float* Y, const float* dY, int64_t 
 int pgs_add2(const float* a, const float* b, float* y, int64_t n_elems, void* stream);
 int pgs_cat2(float* a, int32_t ca, float* b, int32_t cb, float* y, int64_t n, int32_t split, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Whole-network executor  (replaces the per-module Python dispatch of MinkowskiUnet.forward and of the autograd
+ *                          backward through it; reference: torch_points3d/applications/minkowski.py:160-196,
+ *                          modules/MinkowskiEngine/api_modules.py:76-82,281-285,306-311)
+ *
+ * The U-Net's structure is static: a tape of conv / bn(+relu) / add / cat ops over numbered feature slots (slot 0 =
+ * network input).  The host fills one record per convolution / batch norm with this step's device pointers (weights,
+ * kernel-map tables, arranged-weight scratch) and calls ONE function per direction; the functions only walk the tape
+ * and launch the kernels declared above on `stream` (no allocation, no synchronisation, nothing data dependent).
+ * All arrays of these two calls are HOST arrays; the pointers inside the records are device pointers.
+ *
+ * kind_f / kind_b select the conv entry point: 0 pgs_conv_fwd (FFMA), 1 pgs_conv_fwd_tc, 2 pgs_conv_fwd_mma,
+ * 3 pgs_conv_fwd_mma_split.  For 1..3 the arranged weights must already be in wprep_f / wprep_b
+ * (pgs_conv_prep_weights_batch).  nbr_* == NULL: K == 1 identity map.
+ * ------------------------------------------------------------------------------------------ */
+#define PGS_OP_CONV 0
+#define PGS_OP_BN 1
+#define PGS_OP_ADD 2
+#define PGS_OP_CAT 3
+
+typedef struct {
+  int32_t kind, a, b, dst; /* b = -1 unless add / cat */
+  int32_t idx;             /* index into convs / bns */
+  int32_t relu;            /* bn: fuse max(., 0) */
+} pgs_unet_op;
+
+typedef struct {
+  const float* W;          /* fp32 [K, c_in, c_out] */
+  float* dW;               /* accumulated into (caller zeroes); NULL: no weight gradient */
+  const int32_t* nbr_f;    /* forward gather table (rows of the output map) and its occupancy order (or NULL) */
+  const int32_t* order_f;
+  const int32_t* nbr_b;    /* sibling table for the input gradient (rows of the input map) */
+  const int32_t* order_b;
+  const int32_t* pair_in;  /* pgs_kmap_pairs of the forward table (weight gradient); NULL with K == 1 */
+  const int32_t* pair_out;
+  const int32_t* pair_offs;
+  void* wprep_f;           /* arranged weights, forward / backward layout */
+  void* wprep_b;
+  uint64_t wprep_bytes;
+  int64_t max_pairs;
+  int32_t K, c_in, c_out;
+  int32_t kind_f, kind_b;
+  int32_t mirror_f, mirror_b;
+  int32_t need_dx;         /* 0: skip the input gradient (network input that needs none) */
+} pgs_unet_conv;
+
+typedef struct {
+  const float* weight;
+  const float* bias;
+  float* running_mean;
+  float* running_var;
+  float* dweight;          /* NULL: not needed */
+  float* dbias;
+  float momentum, eps;
+  int32_t training;
+  int32_t accumulate;      /* dweight / dbias += (they alias param.grad) instead of = */
+} pgs_unet_bn;
+
+/* sizeof(pgs_unet_op), sizeof(pgs_unet_conv), sizeof(pgs_unet_bn): lets a foreign-language binding verify its mirrors */
+void pgs_unet_record_bytes(int32_t* out3);
+
+/* slot_ptr[s]: fp32 [slot_n[s], slot_c[s]] activation of slot s (slot 0 = input, the rest caller-allocated).
+ * sums: fp64, zeroed by the caller; stats: fp32; both indexed by stat_off[bn] (2*C entries per batch norm). */
+int pgs_unet_forward(const pgs_unet_op* ops, int32_t n_ops, int32_t n_slots,
+                     float* const* slot_ptr, const int64_t* slot_n, const int32_t* slot_c,
+                     const pgs_unet_conv* convs, const pgs_unet_bn* bns,
+                     double* sums, float* stats, const int64_t* stat_off, void* stream);
+
+/* Tape in reverse.  d_out: gradient of slot `out_slot`.  garena: scratch for every intermediate gradient
+ * (pgs_unet_backward_scratch_elems floats).  Weight gradients run on `side_stream` when it is non-NULL (they only
+ * depend on a layer's input activation and output gradient); the function makes `stream` wait for them before it
+ * returns.  grad_in receives the gradient(s) of slot 0 (device pointers into garena, to be summed; at most 8) and
+ * *n_grad_in their number (0 when no convolution reading slot 0 has need_dx). */
+int64_t pgs_unet_backward_scratch_elems(const pgs_unet_op* ops, int32_t n_ops, int32_t n_slots,
+                                        const int64_t* slot_n, const int32_t* slot_c);
+int pgs_unet_backward(const pgs_unet_op* ops, int32_t n_ops, int32_t n_slots, int32_t out_slot,
+                      float* const* slot_ptr, const int64_t* slot_n, const int32_t* slot_c,
+                      const pgs_unet_conv* convs, const pgs_unet_bn* bns,
+                      double* sums, const float* stats, const int64_t* stat_off,
+                      const float* d_out, float* garena, int64_t garena_elems,
+                      float** grad_in, int32_t* n_grad_in, void* stream, void* side_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,8 +21,8 @@ def build(force=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     srcs = sorted(os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith(".c"))
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", OUT, *srcs,
-                           "-lm"])
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-pthread", "-o", OUT,
+                           *srcs, "-lm"])
     return OUT
 
 

@@ -10,6 +10,8 @@ from /root/reference and from this image; the reference ships no tests or golden
 the published HDBSCAN* algorithm and is pinned against scikit-learn 1.9's implementation,
 which IS in this image (tests/test_oracle_hdbscan.py): identical float64 core distances, identical MST
 weight multiset, identical label partitions on generic data, sklearn's own known-answer tests.
+Core-distance rank: hdbscan 0.8.27 does not count the sample itself (rank min_samples + 1), scikit-learn does
+(rank min_samples) -- `core_k()`; the default follows hdbscan, the sklearn pinning passes core_includes_self=True.
 
 Canonical tie-break frozen by this project (DESIGN.md "HDBSCAN determinism"): edges of the mutual-reachability
 graph are strictly ordered by (weight, min(a,b), max(a,b)); the MST under a strict order is unique; the
@@ -37,6 +39,10 @@ def _lib():
         lib.ref_core_distances.restype = None
         lib.ref_mst_total_order.argtypes = [P, P, I64, I64, F64, P, P, P]
         lib.ref_mst_total_order.restype = ctypes.c_int
+        lib.big_core_distances.argtypes = [P, I64, I64, I64, P, ctypes.c_int]
+        lib.big_core_distances.restype = ctypes.c_int
+        lib.big_mst_total_order.argtypes = [P, P, I64, I64, F64, P, P, P, ctypes.c_int]
+        lib.big_mst_total_order.restype = ctypes.c_int
         _LIB = lib
     return _LIB
 
@@ -45,23 +51,31 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def core_distances(X, min_samples):
-    """sklearn/cluster/_hdbscan/hdbscan.py:343-358: kneighbors(X, min_samples)[:, -1] (self included)."""
+def core_distances(X, min_samples, threads=None):
+    """Distance to the `min_samples`-th nearest sample COUNTING the sample itself (sklearn/cluster/_hdbscan/
+    hdbscan.py:343-358: kneighbors(X, min_samples)[:, -1]); see core_k() for the rank each library uses."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     core = np.empty(X.shape[0], np.float64)
-    _lib().ref_core_distances(_p(X), X.shape[0], X.shape[1], int(min_samples), _p(core))
+    if threads:      # oracle/c/hdbscan_big.c: the same loop with the rows split over threads (bit-identical)
+        assert _lib().big_core_distances(_p(X), X.shape[0], X.shape[1], int(min_samples), _p(core), int(threads)) == 0
+    else:
+        _lib().ref_core_distances(_p(X), X.shape[0], X.shape[1], int(min_samples), _p(core))
     return core
 
 
-def mst(X, core, alpha=1.0):
-    """Exact mutual-reachability MST under the canonical strict order.  -> u, v (u < v), w; sorted."""
+def mst(X, core, alpha=1.0, threads=None):
+    """Exact mutual-reachability MST under the canonical strict order.  -> u, v (u < v), w; sorted.
+    threads: parallel Prim of oracle/c/hdbscan_big.c (same unique tree: the order is strict)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     n = X.shape[0]
     u = np.empty(max(n - 1, 0), np.int64)
     v = np.empty(max(n - 1, 0), np.int64)
     w = np.empty(max(n - 1, 0), np.float64)
-    rc = _lib().ref_mst_total_order(_p(X), _p(np.ascontiguousarray(core, dtype=np.float64)), n, X.shape[1],
-                                    float(alpha), _p(u), _p(v), _p(w))
+    core = np.ascontiguousarray(core, dtype=np.float64)
+    if threads:
+        rc = _lib().big_mst_total_order(_p(X), _p(core), n, X.shape[1], float(alpha), _p(u), _p(v), _p(w), int(threads))
+    else:
+        rc = _lib().ref_mst_total_order(_p(X), _p(core), n, X.shape[1], float(alpha), _p(u), _p(v), _p(w))
     assert rc == 0
     return u, v, w
 
@@ -236,15 +250,29 @@ def select_and_label(rows, n, cluster_selection_epsilon=0.0, allow_single_cluste
     return labels
 
 
-def fit_predict(X, min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006, alpha=1.0, return_parts=False):
+def core_k(n, min_samples, core_includes_self=False):
+    """Rank (counting the sample itself) of the neighbour whose distance is the core distance.
+    hdbscan 0.8.27 (the library the reference imports; recalled from its source, unverifiable here): `hdbscan()`
+    clamps min_samples to [1, n-1], and every MST front end (KDTreeBoruvkaAlgorithm._compute_bounds:
+    tree.query(k=min_samples+1)[:, min_samples]; _hdbscan_prims_kdtree: query(k=min_samples+1)[:, -1]; generic
+    mutual_reachability: partition(d, min_points)[:, min_points]) takes the min_samples-th neighbour NOT counting
+    the sample => rank min_samples + 1.  scikit-learn's HDBSCAN counts the sample (kneighbors(X, min_samples)[:, -1])
+    => rank min_samples; `core_includes_self=True` selects that convention (used to pin against sklearn)."""
+    if core_includes_self:
+        if min_samples > n:
+            raise ValueError("min_samples must be at most the number of samples")
+        return int(min_samples)
+    return max(min(n - 1, int(min_samples)), 1) + 1
+
+
+def fit_predict(X, min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006, alpha=1.0, return_parts=False,
+                core_includes_self=False, threads=None):
     X = np.ascontiguousarray(X, dtype=np.float64)
     n = X.shape[0]
     if n < 2:
         raise ValueError("HDBSCAN requires more than one sample")
-    if min_samples > n:
-        raise ValueError("min_samples must be at most the number of samples")
-    core = core_distances(X, min_samples)
-    u, v, w = mst(X, core, alpha)
+    core = core_distances(X, core_k(n, min_samples, core_includes_self), threads)
+    u, v, w = mst(X, core, alpha, threads)
     left, right, dist, size = single_linkage(u, v, w, n)
     rows = condense_tree(left, right, dist, size, min_cluster_size)
     labels = select_and_label(rows, n, cluster_selection_epsilon)

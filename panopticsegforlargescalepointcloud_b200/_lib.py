@@ -75,6 +75,13 @@ SIGNATURES = {
                                    c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_add2": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pgs_cat2": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
+    "pgs_unet_record_bytes": (None, [c_void_p]),
+    "pgs_unet_forward": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "pgs_unet_backward_scratch_elems": (c_int64, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "pgs_unet_backward": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "pgs_conv_bwd_weight": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                     c_int32, c_int32, c_int32, c_void_p, c_void_p]),
 }

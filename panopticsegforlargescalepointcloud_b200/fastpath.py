@@ -18,8 +18,10 @@ input / parameter gradients and BN running statistics) and is used whenever the 
 ResNetDown / ResNetUp / ResBlock structure (`Unsupported`).  PGS_FASTPATH=0 disables it.
 """
 import contextlib
+import ctypes
 import os
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -44,6 +46,35 @@ def _side_stream(dev):
 
 OP_CONV, OP_BN, OP_ADD, OP_CAT = 0, 1, 2, 3
 BN_ACC, BN_ZEROED = 1, 2   # include/pgs_b200.h: PGS_BN_ACCUMULATE_PARAM_GRADS, PGS_BN_SUMS_ZEROED
+
+# "native": pass 2 of the forward and the whole backward walk the tape inside libpgs_b200.so (pgs_unet_forward /
+# pgs_unet_backward, csrc/unet_exec.cpp) -- one ctypes call per direction instead of one per op (~500 per step);
+# "python": the per-op loops below (same kernels, same order; used when bench.py records per-launch events).
+EXECUTOR = os.environ.get("PGS_EXECUTOR", "native")
+
+# host mirrors of the records in include/pgs_b200.h (8-byte fields first: no padding)
+OP_DT = np.dtype([("kind", "i4"), ("a", "i4"), ("b", "i4"), ("dst", "i4"), ("idx", "i4"), ("relu", "i4")])
+CONV_DT = np.dtype([("W", "u8"), ("dW", "u8"), ("nbr_f", "u8"), ("order_f", "u8"), ("nbr_b", "u8"), ("order_b", "u8"),
+                    ("pair_in", "u8"), ("pair_out", "u8"), ("pair_offs", "u8"), ("wprep_f", "u8"), ("wprep_b", "u8"),
+                    ("wprep_bytes", "u8"), ("max_pairs", "i8"), ("K", "i4"), ("c_in", "i4"), ("c_out", "i4"),
+                    ("kind_f", "i4"), ("kind_b", "i4"), ("mirror_f", "i4"), ("mirror_b", "i4"), ("need_dx", "i4")])
+BN_DT = np.dtype([("weight", "u8"), ("bias", "u8"), ("running_mean", "u8"), ("running_var", "u8"), ("dweight", "u8"),
+                  ("dbias", "u8"), ("momentum", "f4"), ("eps", "f4"), ("training", "i4"), ("accumulate", "i4")])
+KIND_CODE = {"ffma": 0, "tc": 1, "mma": 2, "split": 3}
+
+
+def _vp(arr):
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+def _table_ptrs(km, kind, n_q):
+    """(table, order) device pointers a conv kernel of `kind` reads for kernel map `km` (me._conv_launch's rule)."""
+    if km is None:
+        return 0, 0
+    if kind != "ffma" and ME.SORT_TABLES and n_q >= ME.SORT_MIN_ROWS:
+        ns, order = km.sorted()
+        return ns.data_ptr(), order.data_ptr()
+    return km.nbr.data_ptr(), 0
 
 
 class Unsupported(Exception):
@@ -88,6 +119,8 @@ class Program:
         self.wprep = None        # arranged weights: per conv a forward and a backward slot
         self.wprep_off = None
         self.desc_cache = {}     # (kernel kinds, weight pointers, backward needed) -> device descriptor table
+        self.prep_gen = 0        # bumped by every forward that re-arranges the weights (see _UNetFn.backward)
+        self.ops_np = np.array([(k, a, b, d, i, int(r)) for k, a, b, d, i, r in self.ops], dtype=OP_DT)
 
     def out_tensor_stride(self, ts0):
         ts = {0: ts0}
@@ -275,11 +308,54 @@ class _UNetFn(torch.autograd.Function):
             rc = lib.pgs_conv_prep_weights_batch(ent[0].data_ptr(), ent[1], ent[2], sp)
             if rc:
                 check(rc)
+        prog.prep_gen += 1
         wbase = prog.wprep.data_ptr()
         training = [False] * nbn
         tracked = []
-        # ---- pass 2: launches ----
-        for kind, a, b, dst, idx, relu in prog.ops:
+        for i, m in enumerate(prog.bns):
+            bn = m.bn
+            training[i] = bool(bn.training)
+            if training[i] and bn.num_batches_tracked is not None:
+                tracked.append(bn.num_batches_tracked)
+        native = EXECUTOR == "native" and ME.PROFILE is None
+        rec = None
+        if native:
+            if maps_side:
+                main.wait_stream(side)
+            # ---- pass 2, native: this step's pointers into the host records, then ONE call walks the tape ----
+            cv = np.zeros(nconv, CONV_DT)
+            for i, mod in enumerate(prog.convs):
+                km_f, km_b, mf, mb, K, kind_f, kind_b = cinfo[i]
+                of, ob, sz = prog.wprep_off[i]
+                r = cv[i]
+                r["W"] = params[i].data_ptr()
+                r["wprep_f"], r["wprep_b"], r["wprep_bytes"] = wbase + of, wbase + ob, sz
+                r["K"], r["c_in"], r["c_out"] = K, mod.in_channels, mod.out_channels
+                r["kind_f"], r["kind_b"], r["mirror_f"], r["mirror_b"] = KIND_CODE[kind_f], KIND_CODE[kind_b], mf, mb
+            for op in prog.ops:
+                if op[0] == OP_CONV:
+                    i, a, dst = op[4], op[1], op[3]
+                    km_f, km_b, mf, mb, K, kind_f, kind_b = cinfo[i]
+                    r = cv[i]
+                    r["nbr_f"], r["order_f"] = _table_ptrs(km_f, kind_f, n[dst])
+                    if need_bwd:
+                        r["nbr_b"], r["order_b"] = _table_ptrs(km_b, kind_b, n[a])
+            bv = np.zeros(nbn, BN_DT)
+            for i, m in enumerate(prog.bns):
+                bn = m.bn
+                r = bv[i]
+                r["weight"], r["bias"] = params[nconv + i].data_ptr(), params[nconv + nbn + i].data_ptr()
+                r["running_mean"], r["running_var"] = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                r["momentum"], r["eps"], r["training"] = bn.momentum, bn.eps, int(training[i])
+            rec = (cv, bv, np.array(ptrs, np.uint64), np.array(n, np.int64), np.array(C, np.int32),
+                   np.array(soff[:nbn] if nbn else [0], np.int64))
+            cv, bv, slot_ptr, slot_n, slot_c, soff_np = rec
+            rc = lib.pgs_unet_forward(_vp(prog.ops_np), len(prog.ops), S, _vp(slot_ptr), _vp(slot_n), _vp(slot_c), _vp(cv),
+                                      _vp(bv), sums_p, stats_p, _vp(soff_np), sp)
+            if rc:
+                check(rc)
+        # ---- pass 2, per-op Python loop (bench.py's per-launch event pass; PGS_EXECUTOR=python) ----
+        for kind, a, b, dst, idx, relu in (prog.ops if not native else ()):
             if kind == OP_CONV:
                 mod = prog.convs[idx]
                 km_f, km_b, mf, mb, K, kind_f, kind_b = cinfo[idx]
@@ -290,14 +366,10 @@ class _UNetFn(torch.autograd.Function):
                                 n[dst], mf, False, ptrs[dst], wbase + of, sz, sp, kind=kind_f, prepped=True)
             elif kind == OP_BN:
                 bn = prog.bns[idx].bn
-                tr = bool(bn.training)
-                training[idx] = tr
-                if tr and bn.num_batches_tracked is not None:
-                    tracked.append(bn.num_batches_tracked)
                 Cb = C[a]
                 rc = lib.pgs_bn_forward_ex(ptrs[a], n[a], Cb, params[nconv + idx].data_ptr(),
                                            params[nconv + nbn + idx].data_ptr(), bn.running_mean.data_ptr(),
-                                           bn.running_var.data_ptr(), int(tr), float(bn.momentum), float(bn.eps),
+                                           bn.running_var.data_ptr(), int(training[idx]), float(bn.momentum), float(bn.eps),
                                            int(relu), BN_ZEROED, sums_p + 8 * soff[idx], stats_p + 4 * soff[idx],
                                            stats_p + 4 * (soff[idx] + Cb), ptrs[dst], sp)
                 if rc:
@@ -315,6 +387,7 @@ class _UNetFn(torch.autograd.Function):
         o = prog.out_slot
         out = arena[off[o]:off[o] + n[o] * C[o]].view(n[o], C[o])
         ctx.prog, ctx.rt = prog, (n, C, ptrs, cinfo, soff, training, arena, stats)
+        ctx.rec, ctx.prep = rec, (prog.prep_gen, ent)
         ctx.save_for_backward(X, *params)
         return out
 
@@ -361,6 +434,18 @@ class _UNetFn(torch.autograd.Function):
                 return None
             return P[i].grad.data_ptr() if direct[i] else gflat_p + 4 * goff[i]
 
+        # the arranged-weight buffer belongs to the Program and is rewritten by every forward: if another forward ran
+        # since ours (a second batch, an eval pass), put this graph's backward layouts back first
+        gen, ent = ctx.prep
+        if prog.prep_gen != gen and ent[1]:
+            rc = lib.pgs_conv_prep_weights_batch(ent[0].data_ptr(), ent[1], ent[2], sp)
+            if rc:
+                check(rc)
+            prog.prep_gen += 1
+            ctx.prep = (prog.prep_gen, ent)
+        if ctx.rec is not None and ME.PROFILE is None and ME.PROFILE_DW is None:
+            return _UNetFn._backward_native(ctx, lib, sp, dOut, garena, total, sums_p, stats_p, pgrad, direct, needs,
+                                            need_x, gflat, goff)
         side = sp_side = None
         if DW_SIDE_STREAM:
             main = torch.cuda.current_stream(dev)
@@ -448,6 +533,61 @@ class _UNetFn(torch.autograd.Function):
             for extra in g0[1:]:
                 o2 = (extra - gbase) // 4
                 dX = dX + garena[o2:o2 + n[0] * C[0]].view(n[0], C[0])
+        grads = []
+        for i, p in enumerate(P):
+            if not needs[i] or direct[i]:
+                grads.append(None)
+            else:
+                grads.append(gflat[goff[i]:goff[i + 1]].view(p.shape))
+        return (None, None, None, dX) + tuple(grads)
+
+    @staticmethod
+    def _backward_native(ctx, lib, sp, dOut, garena, total, sums_p, stats_p, pgrad, direct, needs, need_x, gflat, goff):
+        prog = ctx.prog
+        n, C, ptrs, cinfo, soff, training, arena, stats = ctx.rt
+        cv, bv, slot_ptr, slot_n, slot_c, soff_np = ctx.rec
+        dev = dOut.device
+        nconv, nbn = len(prog.convs), len(prog.bns)
+        first_ops = {}
+        for op in prog.ops:
+            if op[0] == OP_CONV:
+                first_ops[op[4]] = op
+        for i in range(nconv):
+            km_f = cinfo[i][0]
+            a = first_ops[i][1]
+            r = cv[i]
+            dw = pgrad(i)
+            r["dW"] = dw or 0
+            r["need_dx"] = int(a != 0 or need_x)
+            if dw and km_f is not None:
+                in_idx, out_idx, offs, max_pairs = km_f.pairs()
+                r["pair_in"], r["pair_out"], r["pair_offs"] = in_idx.data_ptr(), out_idx.data_ptr(), offs.data_ptr()
+                r["max_pairs"] = max_pairs
+        for i in range(nbn):
+            iw, ib = nconv + i, nconv + nbn + i
+            if direct[iw] != direct[ib] and needs[iw] and needs[ib]:
+                raise RuntimeError("batch-norm weight and bias must both have (or both lack) a .grad buffer")
+            r = bv[i]
+            r["dweight"], r["dbias"] = pgrad(iw) or 0, pgrad(ib) or 0
+            r["accumulate"] = int(direct[iw] or direct[ib])
+        side_p = None
+        if DW_SIDE_STREAM:
+            side_p = _lib.c_void_p(_side_stream(dev).cuda_stream)
+        g_in = (ctypes.c_void_p * 8)()
+        n_in = ctypes.c_int32(0)
+        rc = lib.pgs_unet_backward(_vp(prog.ops_np), len(prog.ops), prog.n_slots, prog.out_slot, _vp(slot_ptr), _vp(slot_n),
+                                   _vp(slot_c), _vp(cv), _vp(bv), sums_p, stats_p, _vp(soff_np), dOut.data_ptr(),
+                                   garena.data_ptr(), total, g_in, ctypes.byref(n_in), sp, side_p)
+        if rc:
+            check(rc)
+        dX = None
+        if need_x:
+            gbase = garena.data_ptr()
+            for j in range(n_in.value):
+                o = (g_in[j] - gbase) // 4
+                part = garena[o:o + n[0] * C[0]].view(n[0], C[0])
+                dX = part if dX is None else dX + part
+        P = prog.params
         grads = []
         for i, p in enumerate(P):
             if not needs[i] or direct[i]:

@@ -11,7 +11,8 @@ Install as a drop-in with `sys.modules["hdbscan"] = panopticsegforlargescalepoin
 `fit_predict` accepts a numpy array (returns numpy, like upstream) or a CUDA tensor (returns a CUDA tensor).
 Stages: k-NN core distances + exact mutual-reachability MST on the device in float64 (pgs_hdb_mst), then the
 sequential tree stage on the host over pinned buffers (pgs_hdb_labels_host), labels copied back.
-Semantics frozen in DESIGN.md ("HDBSCAN determinism"): core distance counts the sample itself, edges strictly
+Semantics frozen in DESIGN.md ("HDBSCAN determinism"): core distance = min_samples-th neighbour not counting the
+sample itself (hdbscan 0.8.27; `core_includes_self=True` gives scikit-learn's convention), edges strictly
 ordered by (weight, min id, max id), EOM selection, allow_single_cluster=False.  No CPU implementation of the
 device stages exists in this package.
 """
@@ -25,7 +26,8 @@ from ._lib import check, ptr, stream_ptr
 class HDBSCAN:
     def __init__(self, min_cluster_size=5, min_samples=None, cluster_selection_epsilon=0.0, alpha=1.0,
                  metric="euclidean", core_dist_n_jobs=None, cluster_selection_method="eom",
-                 allow_single_cluster=False, approx_min_span_tree=True, algorithm="best", leaf_size=40, **kwargs):
+                 allow_single_cluster=False, approx_min_span_tree=True, algorithm="best", leaf_size=40,
+                 core_includes_self=False, **kwargs):
         if metric != "euclidean":
             raise NotImplementedError("only the euclidean metric is on the reference hot path")
         if cluster_selection_method != "eom":
@@ -36,6 +38,10 @@ class HDBSCAN:
         self.min_samples = self.min_cluster_size if min_samples is None else int(min_samples)
         self.cluster_selection_epsilon = float(cluster_selection_epsilon)
         self.alpha = float(alpha)
+        # hdbscan 0.8.27 takes the min_samples-th neighbour NOT counting the sample itself (all of its MST front ends
+        # query k = min_samples + 1 and read column min_samples); scikit-learn's HDBSCAN counts it.  The default is
+        # the library the reference imports; True = scikit-learn's convention (what the sklearn goldens pin).
+        self.core_includes_self = bool(core_includes_self)
         self.labels_ = None
         self.mst_ = None
         self.core_distances_ = None
@@ -50,8 +56,12 @@ class HDBSCAN:
             raise ValueError("HDBSCAN requires more than one sample")
         if not 1 <= D <= 8:
             raise NotImplementedError("1..8 feature dimensions are supported (the reference uses 3 and 5)")
-        # hdbscan.hdbscan_(): min_samples = min(n - 1, min_samples), at least 1
+        # hdbscan.hdbscan_(): min_samples = min(n - 1, min_samples), at least 1; k = rank counting the sample itself
         k = max(min(n - 1, self.min_samples), 1)
+        if not self.core_includes_self:
+            k += 1
+        if k > 32:
+            raise NotImplementedError("min_samples > 31 is not supported by the device k-NN sweep")
         core = torch.empty(n, dtype=torch.float64, device=dev)
         u = torch.empty(n - 1, dtype=torch.int32, device=dev)
         v = torch.empty(n - 1, dtype=torch.int32, device=dev)

@@ -244,7 +244,9 @@ class BaseModel(nn.Module):
         self._num_batches += 1
         self._num_samples += batch_size
 
-    optimize_parameters = optimize_parameters2
+    def optimize_parameters(self, epoch, batch_size):
+        """base_model.py: the older two-argument entry point (no step index)."""
+        return self.optimize_parameters2(epoch, self._num_batches, batch_size)
 
 
 # --------------------------------------------------------------------------------------------
@@ -299,7 +301,7 @@ class _PanopticBase(BaseModel):
         kw = dict(ignore_labels=self._stuff_classes.to(self.device), radius=self.opt.cluster_radius_search,
                   min_cluster_size=10)
         if nsample is not None:
-            kw["nsample"] = nsample   # raw-position call sites omit it => tpk default 16 (PointGroup3heads.py:185-192)
+            kw["nsample"] = nsample   # raw-position call sites omit it => tpk default 300 (PointGroup3heads.py:185-192)
         return tpk.region_grow(pos, predicted_labels, self.input.batch, **kw)
 
     def _thing_mask(self, predicted_labels):
@@ -347,7 +349,8 @@ class _PanopticBase(BaseModel):
         c_pos = self._region_grow(self.raw_pos, pred)
         c_vote = self._region_grow(self.raw_pos + offset_logits.detach(), pred, nsample=200)
         ctype = torch.zeros(len(c_pos) + len(c_vote), dtype=torch.uint8, device=self.device)
-        ctype[len(c_pos):] = 1
+        if len(c_pos):   # upstream marks the vote clusters only when raw-position growing found something
+            ctype[len(c_pos):] = 1
         return c_pos + c_vote, ctype
 
     def _cluster_hdbscan_embed(self, semantic_logits, embed_logits):               # pointgroupembed._cluster14

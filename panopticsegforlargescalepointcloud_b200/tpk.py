@@ -131,9 +131,12 @@ def grow_labels(pos, gid, radius, nsample):
     return label[:n], nbr, cnt
 
 
-def region_grow(pos, labels, batch, ignore_labels=[], nsample=16, radius=0.02, min_cluster_size=32) -> List[torch.Tensor]:
+def region_grow(pos, labels, batch, ignore_labels=[], nsample=300, radius=0.03, min_cluster_size=50) -> List[torch.Tensor]:
     """PointGroup region growing (tpk signature).  Returns index tensors (int64, on pos.device) into `pos`:
-    classes in ascending order, inside a class clusters by ascending seed (= smallest member), members ascending."""
+    classes in ascending order, inside a class clusters by ascending seed (= smallest member), members ascending.
+    Defaults are those of torch-points-kernels 0.7.0 `region_grow` (nsample=300, radius=0.03, min_cluster_size=50;
+    16 / 0.02 / 32 are the defaults of its `grow_proximity` helper, not of this function): the reference's
+    raw-position call sites omit nsample (PointGroup3heads.py:185-192,250-257,340-347) and therefore run with 300."""
     if labels.dim() != 1 or pos.dim() != 2 or pos.shape[0] != labels.shape[0]:
         raise ValueError("pos [N,3] and labels [N] are required")
     p = _as_f32_pos(pos)

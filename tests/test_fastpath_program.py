@@ -79,3 +79,47 @@ def test_forced_kernels_fall_back_where_unsupported(monkeypatch):
     assert me._conv_kernel_choice(lib, 27, 96, 112, 9000, True) == "tc"
     monkeypatch.setattr(me, "CONV_IMPL", "ffma")
     assert me._conv_kernel_choice(lib, 27, 16, 16, 200000, True) == "ffma"
+
+
+def test_native_executor_records_match_the_header():
+    """The numpy mirrors of pgs_unet_op / pgs_unet_conv / pgs_unet_bn (fastpath.OP_DT / CONV_DT / BN_DT) have the
+    C structs' sizes, and the host-only parts of the executor (scratch sizing, argument checks) agree with Python."""
+    import ctypes
+    import numpy as np
+    from panopticsegforlargescalepointcloud_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 3)()
+    lib.pgs_unet_record_bytes(out)
+    assert list(out) == [fastpath.OP_DT.itemsize, fastpath.CONV_DT.itemsize, fastpath.BN_DT.itemsize]
+    net = bb.Minkowski("unet", input_nc=4, config=bb.paper_backbone_config(16))
+    p = fastpath.Program(net)
+    assert p.ops_np.dtype == fastpath.OP_DT and len(p.ops_np) == len(p.ops)
+    # shapes of a made-up hierarchy: level sizes shrink by ~4x per stride-2 conv
+    n, C, ts = [0] * p.n_slots, [0] * p.n_slots, [1] * p.n_slots
+    n[0], C[0] = 1000, 4
+    size = {1: 1000, 2: 260, 4: 70, 8: 20, 16: 7, 32: 3, 64: 1}
+    for kind, a, b, dst, idx, relu in p.ops:
+        ts[dst], n[dst], C[dst] = ts[a], n[a], C[a]
+        if kind == fastpath.OP_CONV:
+            m = p.convs[idx]
+            ts[dst] = ts[a] // m.stride if m.TRANSPOSE else ts[a] * m.stride
+            n[dst], C[dst] = size[ts[dst]], m.out_channels
+        elif kind == fastpath.OP_CAT:
+            C[dst] = C[a] + C[b]
+    total = 0
+    for kind, a, b, dst, idx, relu in p.ops:
+        if kind in (fastpath.OP_CONV, fastpath.OP_BN):
+            total += n[a] * C[a]
+        elif kind == fastpath.OP_CAT:
+            total += n[a] * (C[a] + C[b])
+    total += sum((c - 1) * n[s] * C[s] for s, c in enumerate(p.consumers) if c > 1)
+    sn, sc = np.array(n, np.int64), np.array(C, np.int32)
+    got = lib.pgs_unet_backward_scratch_elems(p.ops_np.ctypes.data, len(p.ops), p.n_slots, sn.ctypes.data, sc.ctypes.data)
+    assert got == total
+    # argument errors are reported before anything is launched (no GPU needed)
+    bad = p.ops_np.copy()
+    bad["dst"][0] = p.n_slots + 5
+    ptrs = np.zeros(p.n_slots, np.uint64)
+    rc = lib.pgs_unet_forward(bad.ctypes.data, len(bad), p.n_slots, ptrs.ctypes.data, sn.ctypes.data, sc.ctypes.data,
+                              None, None, None, None, None, None)
+    assert rc != 0 and b"slot out of range" in lib.pgs_last_error()

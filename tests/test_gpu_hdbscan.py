@@ -63,7 +63,7 @@ def test_labels_match_sklearn_up_to_ties(cuda_device, eps):
     X = _blobs(41, n=4000, d=5, centers=12)
     ref = SK(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=eps, algorithm="kd_tree", copy=True).fit_predict(
         X.astype(np.float64))
-    m = hdb.HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=eps)
+    m = hdb.HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=eps, core_includes_self=True)
     got = m.fit_predict(X)                      # numpy in -> numpy out, like upstream
     assert isinstance(got, np.ndarray)
     u, v, w = (t.cpu().numpy() for t in m.mst_)
@@ -153,3 +153,40 @@ def test_c3_shape_embeddings_100k(cuda_device):
     pure = [np.bincount(inst[lab == l]).max() / (lab == l).sum() for l in ids]
     assert np.mean(pure) > 0.95
     assert m.boruvka_rounds_ <= 32
+
+
+@pytest.mark.parametrize("name", ["50k", "350k"])
+def test_partition_exact_at_benchmark_size(cuda_device, name):
+    """north_star: bit-exact instance partitions at the C3 size (~350 k thing points x 5-D per FOR-instance cylinder).
+    The CPU oracle's answer (multithreaded exact kNN + Prim, oracle/c/hdbscan_big.c; ~5 min at 350 k) is frozen in
+    tests/golden/hdbscan_big_*.npz by scripts/make_golden_hdbscan_big.py; inputs come from an integer-only generator
+    and are bit-identical on every machine (checked by digest).  Core distances, the canonical MST (edges, weights,
+    order) and the labels must all be EXACTLY the oracle's."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import hdb_big_inputs as inp
+    hdb = _hdb()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hdbscan_big_%s.npz" % name))
+    X, owner = inp.make(name)
+    assert inp.digest(X) == str(g["x_sha"])
+    m = hdb.HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006)
+    lab = m.fit_predict(torch.from_numpy(X).to(cuda_device)).cpu().numpy()
+    u, v, w = (t.cpu().numpy() for t in m.mst_)
+    assert inp.digest(m.core_distances_.cpu().numpy()) == str(g["core_sha"])
+    assert float(w.max()) == float(g["w_max"])
+    assert inp.digest(u.astype(np.int32), v.astype(np.int32), w) == str(g["mst_sha"])
+    assert np.array_equal(lab, g["labels"].astype(np.int64))
+    assert m.n_clusters_ == int(g["n_clusters"])
+
+
+def test_core_rank_convention(cuda_device):
+    """Default = hdbscan 0.8.27's rank (sample not counted) == scikit-learn's convention with min_samples + 1."""
+    hdb = _hdb()
+    X = torch.from_numpy(_blobs(5, n=1500)).to(cuda_device)
+    a = hdb.HDBSCAN(15, 5, 0.006)
+    b = hdb.HDBSCAN(15, 6, 0.006, core_includes_self=True)
+    la, lb = a.fit_predict(X), b.fit_predict(X)
+    assert torch.equal(la, lb) and torch.equal(a.core_distances_, b.core_distances_)
+    c = hdb.HDBSCAN(15, 5, 0.006, core_includes_self=True)
+    c.fit_predict(X)
+    assert bool((c.core_distances_ <= a.core_distances_).all()) and not torch.equal(c.core_distances_, a.core_distances_)

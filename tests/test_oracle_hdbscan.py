@@ -67,7 +67,7 @@ def test_sklearn_known_answer():
     from sklearn.preprocessing import StandardScaler
     X = StandardScaler().fit_transform(X)
     ref = HDBSCAN().fit_predict(X)                     # defaults: min_cluster_size=5, min_samples=None -> 5
-    got = hr.fit_predict(X, min_cluster_size=5, min_samples=5, cluster_selection_epsilon=0.0)
+    got = hr.fit_predict(X, min_cluster_size=5, min_samples=5, cluster_selection_epsilon=0.0, core_includes_self=True)
     assert len(set(got) - {-1}) == 3
     assert _same_partition(got, ref)
 
@@ -101,14 +101,14 @@ def test_labels_match_sklearn(seed, eps):
     X = _blobs(10 + seed, n=500 + 40 * seed, d=5 if seed % 2 == 0 else 3)
     ref = HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=eps, algorithm="kd_tree").fit_predict(
         X.astype(np.float64))
-    got, parts = hr.fit_predict(X, 15, 5, eps, return_parts=True)
+    got, parts = hr.fit_predict(X, 15, 5, eps, return_parts=True, core_includes_self=True)
     assert len(set(ref) - {-1}) >= 2
     assert _same_partition_up_to_ties(got, ref, parts)
 
 
 def test_degenerate_inputs():
     X = np.zeros((40, 3), np.float32)                 # all duplicates: distances 0, lambda = inf
-    got = hr.fit_predict(X, 15, 5, 0.006)
+    got = hr.fit_predict(X, 15, 5, 0.006, core_includes_self=True)
     ref = HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006).fit_predict(X.astype(np.float64))
     assert _same_partition(got, ref)
     X = _blobs(3, n=20)                               # fewer points than any cluster could hold
@@ -123,3 +123,52 @@ def test_cluster_single_contract():
     assert len(out) >= 2 and types == [7] * len(out)
     for c in out:
         assert len(set(batch[c - 1000])) == 1 and len(c) >= 15
+
+
+def test_core_rank_convention():
+    """hdbscan 0.8.27 (what the reference imports) takes the min_samples-th neighbour NOT counting the sample;
+    scikit-learn counts it.  Default = hdbscan's rank, which is scikit-learn's with min_samples + 1."""
+    X = _blobs(21, n=700)
+    n = len(X)
+    assert hr.core_k(n, 5) == 6 and hr.core_k(n, 5, core_includes_self=True) == 5
+    assert hr.core_k(4, 5) == 4            # hdbscan(): min_samples = min(n - 1, min_samples), then + 1 for the rank
+    lab, parts = hr.fit_predict(X, 15, 5, 0.006, return_parts=True)
+    ref_core = NearestNeighbors(n_neighbors=6, algorithm="kd_tree").fit(X.astype(np.float64)).kneighbors(
+        X.astype(np.float64), 6)[0][:, -1]          # 5 other samples + the sample itself
+    assert np.array_equal(parts["core"], ref_core)
+    assert np.array_equal(lab, hr.fit_predict(X, 15, 6, 0.006, core_includes_self=True))
+    ref = HDBSCAN(min_cluster_size=15, min_samples=6, cluster_selection_epsilon=0.006, algorithm="kd_tree").fit_predict(
+        X.astype(np.float64))
+    lab2, parts2 = hr.fit_predict(X, 15, 6, 0.006, return_parts=True, core_includes_self=True)
+    assert _same_partition_up_to_ties(lab2, ref, parts2)
+
+
+def test_threaded_oracle_is_bit_identical():
+    X = _blobs(31, n=3000, centers=9)
+    a, pa = hr.fit_predict(X, 15, 5, 0.006, return_parts=True)
+    b, pb = hr.fit_predict(X, 15, 5, 0.006, return_parts=True, threads=4)
+    assert np.array_equal(a, b)
+    for k in ("core", "u", "v", "w"):
+        assert np.array_equal(pa[k], pb[k])
+
+
+def test_benchmark_size_golden_50k():
+    """tests/golden/hdbscan_big_50k.npz (scripts/make_golden_hdbscan_big.py) is what the oracle computes today, and the
+    integer-only input generator reproduces the frozen inputs bit for bit on this machine."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import hdb_big_inputs as inp
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hdbscan_big_50k.npz"))
+    X, owner = inp.make("50k")
+    assert inp.digest(X) == str(g["x_sha"])
+    lab, parts = hr.fit_predict(X, 15, 5, 0.006, return_parts=True, threads=os.cpu_count())
+    assert np.array_equal(lab, g["labels"].astype(np.int64))
+    assert inp.digest(parts["core"]) == str(g["core_sha"])
+    assert inp.digest(parts["u"].astype(np.int32), parts["v"].astype(np.int32), parts["w"]) == str(g["mst_sha"])
+    # the recovered clusters are the planted trees
+    ids = [l for l in np.unique(lab) if l >= 0]
+    pure = []
+    for l in ids:
+        own = owner[(lab == l) & (owner >= 0)]
+        pure.append(np.bincount(own).max() / len(own) if len(own) else 0.0)    # (a cluster of background points: 0)
+    assert len(ids) >= 20 and np.mean(pure) > 0.9 and np.median(pure) > 0.99

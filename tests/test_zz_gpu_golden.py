@@ -24,7 +24,7 @@ def test_meanshift_vs_golden(cuda_device, i):
 def test_hdbscan_vs_golden(cuda_device, i):
     from panopticsegforlargescalepointcloud_b200 import hdbscan
     g = load("hdbscan")
-    m = hdbscan.HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006)
+    m = hdbscan.HDBSCAN(min_cluster_size=15, min_samples=5, cluster_selection_epsilon=0.006, core_includes_self=True)
     got = m.fit_predict(g["X%d" % i])                      # numpy in -> numpy out, like upstream
     u, v, w = (t.cpu().numpy() for t in m.mst_)
     assert _same_partition_up_to_ties(got, g["labels%d" % i], dict(u=u, v=v, w=w))
