@@ -205,3 +205,59 @@ def step_loss(sd, cfg, batch, weights, training=True, has_offset=True, has_embed
         loss = loss + weights["embedding_loss"] * discriminative_loss_ref(emb[im], batch.instance_labels[im],
                                                                           batch.batch[im])
     return loss, sem, off, emb
+
+
+# ------------------------------------------------------------------------------------------------
+# ScoreNet + score loss  (reference: models/panoptic/PointGroup3heads.py:393-454 `_compute_score`, scorer_type
+# "unet"; core/losses/panoptic_losses.py:25-37 `instance_ious` -> torch_points_kernels.instance_iou, :92-114
+# `instance_iou_loss`; combined at PointGroup3heads.py:593-623).  Written with the reference's explicit per-proposal
+# loops -- the product batches them.
+# ------------------------------------------------------------------------------------------------
+def score_forward(sd, scorer_cfg, backbone_features, coords_xyz, clusters, training=True):
+    """-> (cluster_scores [n_prop], per-row scorer features).  Proposal i becomes batch id i of a second sparse tensor
+    built from the proposal's voxel coordinates (PointGroup3heads.py:402-416), run through ScorerUnet, max-pooled per
+    proposal (scatter max, :436-438) and scored by Linear + Sigmoid (ScorerHead, :51,440)."""
+    xs, cs = [], []
+    for i, c in enumerate(clusters):
+        c = torch.as_tensor(c, dtype=torch.long)
+        xs.append(backbone_features[c])
+        cc = np.asarray(coords_xyz)[c.numpy()]
+        cs.append(np.concatenate([np.full((len(c), 1), i, np.int32), cc.astype(np.int32)], 1))
+    x = torch.cat(xs)
+    coords = np.concatenate(cs, 0)
+    out = unet_forward(sd, scorer_cfg, x, coords, training=training, prefix="ScorerUnet.")
+    feats, start = [], 0
+    for c in clusters:
+        feats.append(out[start:start + len(c)].max(0)[0])
+        start += len(c)
+    feats = torch.stack(feats)
+    scores = torch.sigmoid(feats @ sd["ScorerHead.0.weight"].t() + sd["ScorerHead.0.bias"]).squeeze(-1)
+    return scores, out
+
+
+def instance_iou_ref(clusters, instance_labels, batch):
+    """torch_points_kernels.instance_iou as the reference uses it (panoptic_losses.py:37): IoU of every proposal with
+    every ground-truth instance (labels 1..M_s per scene, 0 = none) of ITS scene, scenes concatenated; 0 elsewhere."""
+    il, b = np.asarray(instance_labels), np.asarray(batch)
+    nb = int(b.max()) + 1
+    per_scene = [int(il[b == s].max()) if (b == s).any() else 0 for s in range(nb)]
+    offs = np.concatenate([[0], np.cumsum(per_scene)])
+    out = np.zeros((len(clusters), int(offs[-1])), np.float32)
+    for p, c in enumerate(clusters):
+        c = np.asarray(c)
+        s = int(b[c[0]])
+        for inst in range(1, per_scene[s] + 1):
+            gt = (b == s) & (il == inst)
+            inter = int(gt[c].sum())
+            out[p, offs[s] + inst - 1] = inter / float(len(c) + int(gt.sum()) - inter)
+    return out
+
+
+def score_loss_ref(ious, scores, lo=0.25, hi=0.75):
+    """panoptic_losses.py:92-114 with its three masks."""
+    best = torch.as_tensor(ious).max(1)[0]
+    shat = torch.zeros_like(best)
+    mid = (best >= lo) & (best <= hi)
+    shat[best > hi] = 1.0
+    shat[mid] = (best[mid] - lo) / (hi - lo)
+    return F.binary_cross_entropy(scores, shat)

@@ -502,8 +502,13 @@ class MinkowskiConvolutionBase(nn.Module):
         super().__init__()
         if dimension is not None and dimension != 3:
             raise NotImplementedError("only 3-D sparse convolution is supported")
-        if kernel_generator is not None or expand_coordinates:
-            raise NotImplementedError("custom kernel generators / coordinate expansion are not supported")
+        if expand_coordinates:
+            raise NotImplementedError("coordinate expansion is not supported")
+        if kernel_generator is not None:      # a plain hyper-cube generator only restates the scalar arguments
+            if not isinstance(kernel_generator, KernelGenerator):
+                raise NotImplementedError("custom kernel generators are not supported")
+            kernel_size, stride, dilation = (kernel_generator.kernel_size, kernel_generator.stride,
+                                             kernel_generator.dilation)
         self.in_channels, self.out_channels = int(in_channels), int(out_channels)
         self.kernel_size = _as_int(kernel_size, "kernel_size")
         self.stride = _as_int(stride, "stride")
@@ -707,6 +712,61 @@ class MinkowskiLeakyReLU(nn.Module):
         return x._like(torch.nn.functional.leaky_relu(x.F, self.negative_slope))
 
 
+class MinkowskiSigmoid(nn.Module):
+    def forward(self, x: SparseTensor):
+        return x._like(torch.sigmoid(x.F))
+
+
+class MinkowskiLinear(nn.Module):
+    """nn.Linear on the feature matrix (api_modules.py:129-134, SELayer; not used by the shipped configs)."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+
+    def forward(self, x: SparseTensor):
+        return x._like(self.linear(x.F))
+
+
+class RegionType:
+    """ME.RegionType: modules/MinkowskiEngine/common.py:53-62 builds lookup tables from these at import time.
+    Only HYPER_CUBE kernels exist on the reference hot path."""
+    HYPER_CUBE, HYPER_CROSS, CUSTOM = 0, 1, 2
+
+
+class KernelGenerator:
+    """ME.KernelGenerator(kernel_size, stride, dilation, region_type=, dimension=): accepted by the convolutions when it
+    describes a plain hyper-cube (modules/MinkowskiEngine/common.py:117-146)."""
+
+    def __init__(self, kernel_size=-1, stride=1, dilation=1, is_transpose=False, region_type=RegionType.HYPER_CUBE,
+                 region_offsets=None, axis_types=None, dimension=3, **_ignored):
+        if region_type != RegionType.HYPER_CUBE or region_offsets is not None or axis_types is not None:
+            raise NotImplementedError("only hyper-cube kernels are on the reference hot path")
+        self.kernel_size, self.stride, self.dilation, self.dimension = kernel_size, stride, dilation, dimension
+        self.region_type = region_type
+
+
+def _not_on_hot_path(name):
+    class _Stub(nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def forward(self, *a, **k):
+            raise NotImplementedError("%s is not on the reference hot path (SURVEY 2.1: SE / pooling variants are "
+                                      "not selected by any shipped panoptic config)" % name)
+    _Stub.__name__ = _Stub.__qualname__ = name
+    return _Stub
+
+
+# symbols the reference's model zoo names at import / construction time but never runs on the panoptic path
+MinkowskiGlobalPooling = _not_on_hot_path("MinkowskiGlobalPooling")
+MinkowskiGlobalMaxPooling = _not_on_hot_path("MinkowskiGlobalMaxPooling")
+MinkowskiBroadcastMultiplication = _not_on_hot_path("MinkowskiBroadcastMultiplication")
+MinkowskiAvgPooling = _not_on_hot_path("MinkowskiAvgPooling")
+MinkowskiSumPooling = _not_on_hot_path("MinkowskiSumPooling")
+MinkowskiAvgUnpooling = _not_on_hot_path("MinkowskiAvgUnpooling")
+
+
 def _fans(tensor):
     if tensor.dim() < 2:
         raise ValueError("fan in / fan out need at least 2 dimensions")
@@ -726,5 +786,12 @@ def kaiming_normal_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
 
 
 utils = types.SimpleNamespace(kaiming_normal_=kaiming_normal_)
+
+# `import MinkowskiEngine.MinkowskiOps as me` / `import MinkowskiEngine.MinkowskiFunctional as MEF` in the reference's
+# stock model zoo (modules/MinkowskiEngine/res16unet.py:5, resunet.py:3): registered as sub-modules by bind.install()
+MinkowskiOps = types.ModuleType("MinkowskiEngine.MinkowskiOps")
+MinkowskiOps.cat = cat
+MinkowskiFunctional = types.ModuleType("MinkowskiEngine.MinkowskiFunctional")
+MinkowskiFunctional.relu = lambda x, *a, **k: x._like(torch.relu(x.F))
 
 __version__ = "0.5.4+b200"

@@ -79,7 +79,7 @@ def test_cluster_and_score_path(cuda_device):
     pred = out.semantic_logits.argmax(1).cpu().numpy()
     ignore = [-1] + list(scenes.stuff_classes("urban"))
     shifted = (model.raw_pos + out.offset_logits.detach()).cpu().numpy()
-    want = tpk_ref.region_grow(batch.pos, pred, batch.batch, ignore, 16, 0.3, 10, method="grid") + \
+    want = tpk_ref.region_grow(batch.pos, pred, batch.batch, ignore, 300, 0.3, 10, method="grid") + \
         tpk_ref.region_grow(shifted, pred, batch.batch, ignore, 200, 0.3, 10, method="grid")
     got = out.clusters or []
     assert [tuple(c.cpu().tolist()) for c in got] == tpk_ref.partition_key(want)
@@ -171,3 +171,55 @@ def test_meanshift_cluster_types(cuda_device, cls, ct):
         assert set(types[:n_rg].tolist()) <= {0, 1}
     for a, b in zip(out.clusters[n_rg:], want):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_scorenet_and_score_loss_parity(cuda_device):
+    """a9 (PointGroup3heads.py:393-454 `_compute_score`, panoptic_losses.py:25-37,92-114): the product batches all
+    proposals into one second sparse tensor (batch id = proposal id, stride-2 first conv on a fresh coordinate hash);
+    the oracle restates the reference's per-proposal loops.  Same proposals (region growing on synthetic head outputs,
+    itself covered above), same weights: scores, IoU matrix and score loss must agree, and so must the gradient the
+    score loss sends into ScorerUnet."""
+    panoptic, scenes = _pkg()
+    from panopticsegforlargescalepointcloud_b200 import tpk, backbone as bb
+    sc = [scenes.make_scene("urban", 8000, 0.2, 5.0, seed=21 + i) for i in range(2)]
+    batch = scenes.collate(sc)
+    heads = [scenes.synthetic_head_outputs(s, seed=21 + i) for i, s in enumerate(sc)]
+    shifted = np.concatenate([s.pos + h[0] for s, h in zip(sc, heads)]).astype(np.float32)
+    pred = np.concatenate([h[2].argmax(1) for h in heads]).astype(np.int64)
+    ignore = [-1] + list(scenes.stuff_classes("urban"))
+    props = tpk.region_grow(torch.from_numpy(shifted).to(cuda_device), torch.from_numpy(pred).to(cuda_device),
+                            torch.as_tensor(batch.batch).to(cuda_device), ignore_labels=ignore, nsample=200, radius=0.3,
+                            min_cluster_size=10)
+    assert len(props) >= 10
+    torch.manual_seed(2022)
+    opt = panoptic.paper_options("urban", cluster_type=1, grid=0.2, prepare_epoch=-1, backbone="two_level")
+    model = panoptic.PointGroup3heads(opt, "dummy", panoptic.DatasetProperties("urban"), None).to(cuda_device)
+    model.eval()                                                   # running statistics: a well-conditioned comparison
+    model._do_cluster = lambda sem, off, emb: (props, torch.zeros(len(props), dtype=torch.uint8, device=cuda_device))
+    model.set_input(batch, cuda_device)
+    out = model.forward(epoch=31)
+    model.zero_grad()
+    model.backward(31)
+    assert out.cluster_scores is not None and out.cluster_scores.shape[0] == len(props)
+
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    cb = _cpu_batch(batch)
+    coords4 = np.concatenate([np.asarray(batch.batch)[:, None], np.asarray(batch.coords)], 1).astype(np.int32)
+    feats = cpu_path.unet_forward(sd, cpu_path.resolve_cfg(opt.backbone.config, 4), cb.x, coords4, training=False,
+                                  prefix="Backbone.")
+    clusters = [c.cpu().numpy() for c in props]
+    scores, _ = cpu_path.score_forward(sd, cpu_path.resolve_cfg(bb.scorer_unet_config(16), 16), feats,
+                                       np.asarray(batch.coords), clusters, training=False)
+    assert float((out.cluster_scores.detach().cpu() - scores.detach()).abs().max()) <= TOL
+    ious = cpu_path.instance_iou_ref(clusters, np.asarray(batch.instance_labels), np.asarray(batch.batch))
+    got_iou = tpk.instance_iou(props, model.input.instance_labels, model.input.batch).cpu().numpy()
+    assert got_iou.shape == ious.shape and np.allclose(got_iou, ious, rtol=0, atol=1e-7)   # integer counts, one division
+    assert ious.max(1).mean() > 0.3                                                 # the proposals do hit instances
+    sl = cpu_path.score_loss_ref(ious, scores)
+    assert abs(float(model.score_loss) - float(sl)) <= TOL * max(1.0, abs(float(sl)))
+    sl.backward()
+    ga = torch.cat([p.grad.cpu().reshape(-1) for n, p in model.ScorerUnet.named_parameters()]).double()
+    gb = torch.cat([sd["ScorerUnet." + n].grad.reshape(-1) for n, p in model.ScorerUnet.named_parameters()]).double()
+    # model.backward adds the other loss terms too, but only the score loss reaches ScorerUnet
+    assert float((ga - gb).norm() / gb.norm()) <= 1e-3

@@ -385,3 +385,115 @@ def test_fused_batchnorm_matches_torch(cuda_device, C, n, relu, training):
     assert torch.allclose(a.bn.running_mean, ref.running_mean, atol=1e-5, rtol=1e-5)
     assert torch.allclose(a.bn.running_var, ref.running_var, atol=1e-5, rtol=1e-4)
     assert int(a.bn.num_batches_tracked) == int(ref.num_batches_tracked)
+
+
+# ------------------------------------------------------------------------------------------------
+# benchmark size (BASELINE configs[1], C2: 200 k-voxel NPM3D-shape cylinder)
+# ------------------------------------------------------------------------------------------------
+_C2 = {}
+
+
+def _c2_scene(dev):
+    if "mgr" not in _C2:
+        me = _me()
+        from panopticsegforlargescalepointcloud_b200 import scenes
+        s = scenes.make_scene("urban", 200000, 0.12, 16.0, seed=0)
+        c = np.concatenate([np.zeros((len(s.coords), 1), np.int32), s.coords], 1)
+        _C2["coords"] = c
+        _C2["mgr"] = me.CoordinateManager(torch.from_numpy(c).to(dev))
+        _C2["maps"] = sr.Maps(c)
+    return _C2["coords"], _C2["mgr"], _C2["maps"]
+
+
+def test_rulebooks_bit_exact_at_benchmark_size(cuda_device):
+    """Level-0 (k3 s1) and level-0 -> 1 (k3 s2, and its transposed sibling) rulebooks of the C2 scene, 200 k rows,
+    against the numpy oracle: coordinate map, gather tables, ME-style pair lists -- all bit-exact."""
+    coords, mgr, maps = _c2_scene(cuda_device)
+    m2, in2out = mgr._build(mgr.maps[1].coords, 2)
+    oc, oi = sr.coordinate_map(coords, 2)
+    assert np.array_equal(m2.coords.cpu().numpy(), oc) and np.array_equal(in2out.cpu().numpy(), oi)
+    mgr.stride(1, 2); maps.stride(1, 2)
+    total = 0
+    for key in ((1, 1, 1, +1, 3), (2, 1, 1, +1, 3), (1, 2, 1, -1, 3)):
+        km = mgr.kernel_map(*key)
+        ref = maps.kernel_map(*key)
+        assert np.array_equal(km.nbr.cpu().numpy(), ref)
+        i, o, offs, mx = km.pairs()
+        ri, ro, roffs = sr.pairs(ref)
+        npairs = int(roffs[-1])
+        assert np.array_equal(offs.cpu().numpy(), roffs)
+        assert np.array_equal(i.cpu().numpy()[:npairs], ri) and np.array_equal(o.cpu().numpy()[:npairs], ro)
+        total += npairs
+    assert total > 2_000_000      # ~1.2 M pairs on the stride-1 map alone (6 per row)
+
+
+@pytest.mark.parametrize("cin,cout,level,impl", [(16, 16, 1, "mma"), (32, 32, 2, "mma"), (64, 64, 1, "tc"),
+                                                 (4, 16, 1, "ffma"), (16, 16, 1, "tc"), (32, 16, 1, "auto")])
+def test_conv_value_parity_at_benchmark_size(cuda_device, monkeypatch, cin, cout, level, impl):
+    """One convolution per kernel family on the 200 k-row C2 map (level 1) / its 100 k-row stride-2 map (level 2):
+    forward, input gradient and weight gradient against a float64 gather-matmul of the same device tensors."""
+    me = _me()
+    coords, mgr, maps = _c2_scene(cuda_device)
+    monkeypatch.setattr(me, "CONV_IMPL", impl)
+    if level == 2:
+        mgr.stride(1, 2)
+    km = mgr.kernel_map(level, level, level, +1, 3)
+    n = km.n_q
+    assert n == (200000 if level == 1 else mgr.maps[2].n) and n > 80000
+    g = torch.Generator(device="cpu").manual_seed(cin * 100 + cout)
+    X = torch.randn(n, cin, generator=g).to(cuda_device).requires_grad_(True)
+    conv = me.MinkowskiConvolution(cin, cout, kernel_size=3, stride=1, dimension=3).to(cuda_device)
+    out = conv(me.SparseTensor(X, coordinate_manager=mgr, tensor_stride=level)).F
+    dY = torch.randn(n, cout, generator=g).to(cuda_device)
+    out.backward(dY)
+    W3 = conv.kernel.detach()
+    Yr = _conv_ref64(X.detach(), W3, km.nbr, n, False, False)
+    dXr = _conv_ref64(dY, W3, km.nbr, n, True, True)
+    dWr = torch.zeros(27, cin, cout, dtype=torch.float64, device=cuda_device)
+    for k in range(27):
+        idx = km.nbr[k].long()
+        m = idx >= 0
+        dWr[k] = X.detach().double()[idx[m]].t() @ dY.double()[m]
+    for got, ref, tol in ((out.detach(), Yr, TOL), (X.grad, dXr, TOL), (conv.kernel.grad, dWr, TOL)):
+        err = float((got.double() - ref).abs().max())
+        assert err <= tol * max(1.0, float(ref.abs().max())), (err, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("executor", ["native", "python"])
+def test_unet_gradient_vs_fp64_oracle(cuda_device, monkeypatch, executor):
+    """End-to-end gradient of the 82-conv network in TRAINING mode (batch statistics) through the fused executor,
+    against a float64 run of the CPU oracle on a scene whose coarsest level still has hundreds of rows.
+    Bounds: every parameter tensor within 3e-2 relative L2 (an fp32 CPU run of the same oracle sits at <= 7e-3: the
+    conv-before-BN weight gradients are sums that cancel by construction), all gradients together: 1 - cos <= 1e-5
+    (fp32 CPU: 1.4e-6); a wrong term in any layer's backward moves that layer's tensors by O(1)."""
+    me = _me()
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb, fastpath
+    monkeypatch.setattr(fastpath, "EXECUTOR", executor)
+    torch.manual_seed(2022)
+    cfg = bb.paper_backbone_config(16)
+    net = bb.Minkowski("unet", input_nc=4, config=cfg).to(cuda_device)
+    net.train()
+    rng = np.random.default_rng(11)
+    coords = _scene(4, n=15000, extent=300)
+    x = rng.standard_normal((len(coords), 4)).astype(np.float32)
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    xin = _batch(coords, x, cuda_device)
+    out = net(xin).x
+    g = torch.from_numpy(rng.standard_normal(tuple(out.shape)).astype(np.float32))
+    out.backward(g.to(cuda_device))
+    assert fastpath.program_for(net) is not None
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v).clone().requires_grad_(
+        v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    ref = cpu_path.unet_forward(sd64, cpu_path.resolve_cfg(cfg, 4), torch.from_numpy(x).double(), coords, training=True)
+    ref.backward(g.double())
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) <= TOL * max(float(ref.detach().abs().max()), 1.0)
+    worst = 0.0
+    for name, p in net.named_parameters():
+        r = sd64[name].grad
+        rel = float((p.grad.cpu().double() - r).norm() / r.norm().clamp_min(1e-30))
+        worst = max(worst, rel)
+        assert rel <= 3e-2, (name, rel)
+    ga = torch.cat([p.grad.cpu().reshape(-1) for _, p in net.named_parameters()]).double()
+    gb = torch.cat([sd64[n].grad.reshape(-1) for n, _ in net.named_parameters()])
+    cos = float(torch.dot(ga, gb) / (ga.norm() * gb.norm()))
+    assert 1.0 - cos <= 1e-5, (cos, worst)
