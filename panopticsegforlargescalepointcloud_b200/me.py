@@ -43,12 +43,19 @@ class KernelMap:
     """Gather table nbr[K, n_q] (+ lazily the ME-style pair lists used by the weight gradient and the
     occupancy-sorted copy used by the tensor-core kernels)."""
 
-    __slots__ = ("nbr", "K", "n_q", "_pairs", "_sorted")
+    __slots__ = ("nbr", "K", "n_q", "_pairs", "_sorted", "_n_pairs")
 
     def __init__(self, nbr, K, n_q):
         self.nbr, self.K, self.n_q = nbr, K, n_q
         self._pairs = None
         self._sorted = None
+        self._n_pairs = None
+
+    def n_pairs(self):
+        """Rulebook size P (host value; synchronises once per kernel map -- bench.py's roofline pass only)."""
+        if self._n_pairs is None:
+            self._n_pairs = int((self.nbr >= 0).sum())
+        return self._n_pairs
 
     def sorted(self):
         """-> (nbr_sorted int32[K, n_q], order int32[n_q]): the table with its rows sorted by their K-bit
@@ -372,7 +379,12 @@ def _conv_launch(lib, Xp, n_in, Wp, K, c_in, c_out, km, n_q, mirror, w_transpose
         check(rc)
     if PROFILE is not None:
         e1.record()
-        pairs = int((nbr >= 0).sum()) if (nbr is not None and PROFILE_COUNT_PAIRS) else (n_q if nbr is None else 0)
+        if nbr is None:
+            pairs = n_q
+        elif not PROFILE_COUNT_PAIRS:
+            pairs = 0
+        else:
+            pairs = km.n_pairs() if isinstance(km, KernelMap) else int((nbr >= 0).sum())
         PROFILE.append((e0, e1, conv_algorithmic_bytes(n_in, n_q, K, c_in, c_out, nbr is not None),
                         2 * pairs * c_in * c_out, (n_in, n_q, K, c_in, c_out), kind))
     return kind

@@ -154,6 +154,14 @@ class _Batch:
         return _Batch(**{k: (v.to(device) if torch.is_tensor(v) else v) for k, v in self.__dict__.items()})
 
 
+def _nll_loss_mean(logp, target, ignore_index):
+    """F.nll_loss(logp, target, ignore_index=..., reduction="mean") (PointGroup3heads.py:554-557) as gather + masked mean:
+    torch's nll_loss reduces [N, C] with a single thread block (0.2 ms forward + 0.1 ms backward per 200 k rows)."""
+    valid = target != ignore_index
+    picked = logp.gather(1, target.clamp_min(0).unsqueeze(1)).squeeze(1)
+    return -(picked * valid).sum() / valid.sum()
+
+
 def _get(data, key):
     v = data[key] if not hasattr(data, key) else getattr(data, key)
     return torch.as_tensor(v) if not torch.is_tensor(v) else v
@@ -418,7 +426,7 @@ class _PanopticBase(BaseModel):
         """PointGroup3heads.py:552-634 (mask loss omitted: mask_supervise is False in every shipped config)."""
         w = self.opt.loss_weights
         inp, out = self.input, self.output
-        self.semantic_loss = nn.functional.nll_loss(out.semantic_logits, inp.y.to(torch.int64), ignore_index=IGNORE_LABEL)
+        self.semantic_loss = _nll_loss_mean(out.semantic_logits, inp.y.to(torch.int64), IGNORE_LABEL)
         self.loss = w["semantic"] * self.semantic_loss
         im = inp.instance_mask
         if self.HAS_OFFSET:

@@ -88,10 +88,19 @@ class DataParallelStep:
                     dist.broadcast(t, src=0)
         model._grad_hook = self._hook
         model._zero_grad_hook = self.bucket.zero   # one memset of the flat buffer instead of one fill per parameter
+        self.allreduce_events = None    # set to a list: (start, end) CUDA events around every gradient all-reduce
 
     def _hook(self):
         self.bucket.check_views()
-        self.bucket.all_reduce_mean()
+        ev = self.allreduce_events
+        if ev is not None and self.bucket.flat.is_cuda and dist.is_initialized() and dist.get_world_size() > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.bucket.all_reduce_mean()
+            e1.record()
+            ev.append((e0, e1))
+        else:
+            self.bucket.all_reduce_mean()
 
     def step(self, data, epoch, step=0, batch_size=1):
         self.model.set_input(data, self.model.device)
