@@ -222,6 +222,17 @@ int pgs_rg_init(const int32_t* gid, int64_t n, int32_t* label, void* stream);
 int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid, int64_t n, int32_t nsample,
                      int32_t rounds, int32_t* label, int32_t* changed, void* stream);
 
+/* Nearest support point of every query (k = 1) on the grid built by pgs_bq_grid_build (cell >= the typical point spacing);
+ * replaces torch_geometric.nn.knn(x, y, k=1) of the eval-time back-projection (reference:
+ * torch_points3d/metrics/panoptic_tracker_pointgroup_npm3d.py:384 (block -> original points), :592 (subsampled -> full
+ * cloud)).  qpos / qkeys from pgs_bq_pack_queries with the SAME cell; meta = the grid's {#support rows, #cells}.
+ *   idx_out int32 [n_q]  support row with the smallest fp32 d2 = fma(dz,dz,fma(dy,dy,dx*dx)), ties to the smaller index
+ *                        (-1: no support point in the query's group);   d2_out fp32 [n_q] that distance (inf if none).
+ * Rings of cells are searched outwards up to max_ring; queries that still found nothing scan all support rows. */
+int pgs_nn1_query(const float* spos, const float* qpos, const uint64_t* qkeys, int64_t n_q,
+                  const uint64_t* tkeys, const int32_t* tvals, int64_t cap, const int32_t* cell_start,
+                  const int32_t* meta, float cell, int32_t max_ring, int32_t* idx_out, float* d2_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * HDBSCAN  (replaces hdbscan.HDBSCAN(min_cluster_size, min_samples, cluster_selection_epsilon).fit_predict --
  *           un-vendored dependency hdbscan 0.8.27; reference: torch_points3d/utils/hdbscan_cluster.py:8-13,

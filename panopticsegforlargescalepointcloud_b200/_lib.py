@@ -38,6 +38,8 @@ SIGNATURES = {
     "pgs_bq_query": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_float,
                              c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_bq_export": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgs_nn1_query": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float,
+                              c_int32, c_void_p, c_void_p, c_void_p]),
     "pgs_rg_init": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pgs_rg_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                  c_void_p]),

@@ -365,6 +365,92 @@ static GridLayout grid_layout(int64_t n, void* base) {
   return L;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Nearest support point per query (k = 1) on the same voxel-hash grid: eval-time back-projection of block / subsampled
+// predictions onto the full cloud (replaces torch_geometric.nn.knn(x, y, k=1) in
+// torch_points3d/metrics/panoptic_tracker_pointgroup_npm3d.py:384,592).
+// One thread per query walks the cube of cells around it ring by ring (Chebyshev radius R = 1, 2, ...): after ring R every
+// unvisited support point is farther than R * cell, so the search stops as soon as the best distance is <= R * cell.
+// Best = smallest fp32 d2 = fma(dz,dz, fma(dy,dy, dx*dx)), ties to the smaller support index (a brute-force scan in
+// index order with a strict `<` keeps exactly that one).  Queries with nothing inside max_ring rings scan all rows.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nn1_scan_cell(const float4* __restrict__ spos, int cur, int end, float qx, float qy,
+                                              float qz, float* best_d2, int* best_id) {
+  for (int i = cur; i < end; ++i) {
+    const float4 p = __ldg(&spos[i]);
+    const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const int id = __float_as_int(p.w);
+    if (d2 < *best_d2 || (d2 == *best_d2 && id < *best_id)) {
+      *best_d2 = d2;
+      *best_id = id;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kCT) nn1_kernel(const float4* __restrict__ spos, const float4* __restrict__ qpos,
+                                                   const uint64_t* __restrict__ qkeys, int64_t n_q,
+                                                   const uint64_t* __restrict__ tkeys, const int32_t* __restrict__ tvals,
+                                                   uint64_t mask, const int32_t* __restrict__ cell_start,
+                                                   const int32_t* __restrict__ meta, float cell, int max_ring,
+                                                   int32_t* __restrict__ idx_out, float* __restrict__ d2_out) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_q) return;
+  const float4 qp = qpos[w];
+  const int q = __float_as_int(qp.w);
+  const uint64_t qk = qkeys[w];
+  float best_d2 = __int_as_float(0x7f800000);   // +inf
+  int best_id = 0x7fffffff;
+  bool done = false;
+  if (qk != kInvalidKey) {
+    const int cx = (int)(qk & 0xffff), cy = (int)((qk >> 16) & 0xffff), cz = (int)((qk >> 32) & 0xffff);
+    const uint64_t ghi = qk & 0xffff000000000000ull;
+    for (int R = 1; R <= max_ring && !done; ++R) {
+      // ring R = cells at Chebyshev distance exactly R (R == 1 also takes the centre cube: distance 0)
+      for (int dz = -R; dz <= R; ++dz)
+        for (int dy = -R; dy <= R; ++dy) {
+          const bool edge_zy = (dz == -R || dz == R || dy == -R || dy == R);
+          const int step = (edge_zy || R == 1) ? 1 : 2 * R;   // interior of the slab: only the two x faces
+          for (int dx = -R; dx <= R; dx += step) {
+            const int x = cx + dx, y = cy + dy, z = cz + dz;
+            if (x < 2 || y < 2 || z < 2 || x > 65534 || y > 65534 || z > 65534) continue;
+            const uint64_t k = ghi | ((uint64_t)(unsigned)z << 32) | ((uint64_t)(unsigned)y << 16) | (uint64_t)(unsigned)x;
+            uint64_t slot = hash64(k) & mask;
+            for (;;) {
+              const uint64_t tk = __ldg(&tkeys[slot]);
+              if (tk == k) {
+                const int c = __ldg(&tvals[slot]);
+                nn1_scan_cell(spos, __ldg(&cell_start[c]), __ldg(&cell_start[c + 1]), qp.x, qp.y, qp.z, &best_d2, &best_id);
+                break;
+              }
+              if (tk == kEmptyKey) break;
+              slot = (slot + 1) & mask;
+            }
+          }
+        }
+      const float reach = (float)R * cell * 0.9999f;   // (margin for the fp32 rounding of d2)
+      if (best_d2 <= reach * reach) done = true;
+    }
+  }
+  if (!done) {   // sparse neighbourhood, or a query outside the packable cell range: exhaustive scan of the support rows
+    const int n_valid = meta[0];   // (single-group contract: callers pass one group; merging.py does)
+    best_d2 = __int_as_float(0x7f800000);
+    best_id = 0x7fffffff;
+    for (int i = 0; i < n_valid; ++i) {
+      const float4 p = __ldg(&spos[i]);
+      const float dx = p.x - qp.x, dy = p.y - qp.y, dz = p.z - qp.z;
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      const int id = __float_as_int(p.w);
+      if (d2 < best_d2 || (d2 == best_d2 && id < best_id)) {
+        best_d2 = d2;
+        best_id = id;
+      }
+    }
+  }
+  idx_out[q] = best_id == 0x7fffffff ? -1 : best_id;
+  d2_out[q] = best_d2;
+}
+
 }  // namespace pgs
 
 using namespace pgs;
@@ -467,6 +553,20 @@ int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid,
     rg_jump_kernel<<<grid_for_c(n), kCT, 0, s>>>(n, label, changed);
     count_launch(2);
   }
+  PGS_CHECK_LAUNCH();
+  return PGS_OK;
+}
+
+int pgs_nn1_query(const float* spos, const float* qpos, const uint64_t* qkeys, int64_t n_q, const uint64_t* tkeys,
+                  const int32_t* tvals, int64_t cap, const int32_t* cell_start, const int32_t* meta, float cell,
+                  int32_t max_ring, int32_t* idx_out, float* d2_out, void* stream) {
+  PGS_CHECK_ARG((cap & (cap - 1)) == 0, "capacity must be a power of two");
+  PGS_CHECK_ARG(cell > 0.f && max_ring >= 1, "cell edge and ring bound must be positive");
+  if (n_q == 0) return PGS_OK;
+  nn1_kernel<<<grid_for_c(n_q), kCT, 0, (cudaStream_t)stream>>>((const float4*)spos, (const float4*)qpos, qkeys, n_q,
+                                                                tkeys, tvals, (uint64_t)(cap - 1), cell_start, meta,
+                                                                cell, max_ring, idx_out, d2_out);
+  count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;
 }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) conv_prep_batch_kernel(const int64_t* __r
   float* dst = (float*)d[1];
   const int K = (int)d[2], C = (int)d[3], N = (int)d[4], wt = (int)d[5], layout = (int)d[6];
   if (layout == 0) {
-    const int64_t total = (int64_t)K * C * N;
+    const int64_t total = 2 * (int64_t)K * C * N;   // hi + lo planes (conv_prep.cuh)
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
       dst[e] = prep_tc_elem(W, K, C, N, wt, e);
   } else {

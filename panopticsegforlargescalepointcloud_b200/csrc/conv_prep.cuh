@@ -7,7 +7,14 @@ namespace pgs {
 
 constexpr int kPrepKC = 16;   // == kTcKC (conv_tc.cu): input channels per tcgen05 pipeline step
 
-// tcgen05 layout:  Wp[k][j][q][n][4] = B_k[n][j*16 + q*4 .. +3]; e enumerates the OUTPUT floats
+__device__ __forceinline__ uint32_t prep_tf32_rn(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+}
+
+// tcgen05 layout:  Wp[k][j][plane][q][n][4] = split_plane(B_k[n][j*16 + q*4 .. +3]); e enumerates the 2*K*C*N OUTPUT
+// floats.  plane 0: hi = rn_tf32(w); plane 1: lo = rn_tf32(w - hi) (w - hi is exact in fp32).  Splitting here, once
+// per step, instead of in the conv kernel at every pipeline step lets the kernel fetch a chunk with one TMA copy.
 __device__ __forceinline__ float prep_tc_elem(const float* __restrict__ W, int K, int C, int N, int w_transposed, int64_t e) {
   const int t = (int)(e & 3);
   int64_t r = e >> 2;
@@ -15,17 +22,16 @@ __device__ __forceinline__ float prep_tc_elem(const float* __restrict__ W, int K
   r /= N;
   const int q = (int)(r & 3);
   r >>= 2;
+  const int plane = (int)(r & 1);
+  r >>= 1;
   const int J = C / kPrepKC;
   const int j = (int)(r % J);
   const int k = (int)(r / J);
   const int c = j * kPrepKC + q * 4 + t;
   // !w_transposed: W stored [K][C][N];  w_transposed: W stored [K][N][C]
-  return w_transposed ? W[((int64_t)k * N + n) * C + c] : W[((int64_t)k * C + c) * N + n];
-}
-
-__device__ __forceinline__ uint32_t prep_tf32_rn(float x) {
-  const uint32_t u = __float_as_uint(x);
-  return (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+  const float w = w_transposed ? W[((int64_t)k * N + n) * C + c] : W[((int64_t)k * C + c) * N + n];
+  const float hi = __uint_as_float(prep_tf32_rn(w));
+  return plane == 0 ? hi : __uint_as_float(prep_tf32_rn(w - hi));
 }
 __device__ __forceinline__ uint32_t prep_pack_bf16(uint32_t first_bits, uint32_t second_bits) {   // first -> low half
   uint32_t d;

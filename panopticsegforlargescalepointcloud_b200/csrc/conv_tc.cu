@@ -8,9 +8,12 @@
 // ALL output channels (UMMA N = Cout, 16..192), so the fp32 accumulator tile D[128 x Cout] lives in tensor
 // memory for the whole walk over the K kernel offsets and Cin/16 channel chunks and every output row is
 // written exactly once (no atomics, deterministic).  Per step the CTA's threads gather 128 rows x 16 input
-// channels through the rulebook table with 16-byte loads, and copy the matching pre-arranged weight chunk;
-// both go to shared memory in the canonical K-major no-swizzle UMMA layout [chunk of 4 floats][row][4].
-// One elected thread issues tcgen05.mma (kind::tf32); tcgen05.commit on an mbarrier recycles the 2-stage ring.
+// channels through the rulebook table with 16-byte loads, split them into tf32 hi / lo and store them to shared
+// memory in the canonical K-major no-swizzle UMMA layout [chunk of 4 floats][row][4] (2-stage ring).  The matching
+// weight chunk -- pre-arranged AND pre-split into hi / lo planes once per step by the prep kernel -- is a contiguous
+// 128 * Cout-byte tile that ONE thread fetches with a TMA tensor copy (cp.async.bulk.tensor.2d -> UTMALDG) into its
+// own 2..4-deep ring, `ring - 2` steps ahead, completing on an mbarrier (expect-tx).  One elected thread issues
+// tcgen05.mma (kind::tf32); tcgen05.commit on an mbarrier recycles both rings.
 //
 // Measured on B200 (scripts/micro/mma_bench.cu, profiles/r1_mma_issue_rate.txt): with both operands in shared
 // memory (SS mode) an M = 128 tcgen05.mma costs >= 97 cycles whatever N <= 96, the layout (interleaved or
@@ -22,6 +25,8 @@
 // Precision: the parity bar is 1e-4 against an fp32 oracle; single-pass tf32 (10-bit mantissa) cannot meet
 // it, so operands are split a = hi + lo (hi = rn_tf32(a), lo = rn_tf32(a - hi)) on the way into shared memory
 // and three MMAs accumulate hi*hi + hi*lo + lo*hi into the same TMEM tile (error ~2^-21 per product).
+#include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint)
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -54,6 +59,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: one box of the 2-D weight tensor (coordinates {0, row}) -> shared memory, bytes counted on `bar`
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -129,14 +145,15 @@ __device__ __forceinline__ void split_store(float4 v, float4* hi_dst, float4* lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight pre-arrangement:  Wp[k][j][q][n][4] = B_k[n][j*16 + q*4 .. +3]   with  B_k = W[k]^T (forward: n = cout,
-// contraction over cin) or B_k = W[k] (input gradient: n = cin, contraction over cout)
+// weight pre-arrangement:  Wp[k][j][plane][q][n][4] = split_plane(B_k[n][j*16 + q*4 .. +3])   with  B_k = W[k]^T
+// (forward: n = cout, contraction over cin) or B_k = W[k] (input gradient: n = cin, contraction over cout);
+// plane 0 = tf32 hi, plane 1 = tf32 lo (conv_prep.cuh).  One (k, j) chunk = 128 * N contiguous bytes = one TMA box.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_tc_prep_weights_kernel(const float* __restrict__ W, int K, int c_in,
                                                                     int c_out, int w_transposed,
                                                                     float* __restrict__ Wp) {
   // kernel-side naming: contraction length C (= c_in of the launch), N output channels (= c_out of the launch)
-  const int64_t total = (int64_t)K * c_in * c_out;
+  const int64_t total = 2 * (int64_t)K * c_in * c_out;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
     Wp[e] = prep_tc_elem(W, K, c_in, c_out, w_transposed, e);
 }
@@ -147,15 +164,17 @@ __global__ void __launch_bounds__(256) conv_tc_prep_weights_kernel(const float* 
 constexpr int kTcMaxK = 27;
 constexpr int kTcPrefetch = 4;   // steps of global loads in flight per thread (register queue)
 
-// NB = float4 weight elements per thread and step: ceil(4 * N / 256) -> 1 (N <= 64), 2 (N <= 128), 3 (N <= 192)
-template <int NB>
-__global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
+constexpr int kTcMaxBRing = 4;
+
+__global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __restrict__ X,
+                                                              const __grid_constant__ CUtensorMap w_map,
                                                               const int32_t* __restrict__ nbr, int64_t n_q, int K,
                                                               int c_in, int c_out, int mirror, uint32_t tmem_cols,
-                                                              int ksplit, const int32_t* __restrict__ order,
+                                                              int ksplit, int bring, const int32_t* __restrict__ order,
                                                               float* __restrict__ Y) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_empty[kTcStages];
+  __shared__ uint64_t bar_full[kTcMaxBRing];
   __shared__ uint64_t bar_done;
   __shared__ uint32_t tmem_base_s;
   __shared__ int idx_all[kTcMaxK][kTcM];
@@ -167,14 +186,18 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
   const int N = c_out;
   const uint32_t a_bytes = kTcM * kTcKC * 4;        // one of hi / lo
   const uint32_t b_bytes = (uint32_t)N * kTcKC * 4;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;   // [A_hi][A_lo][B_hi][B_lo]
+  const uint32_t stage_bytes = 2 * a_bytes;         // A ring: [A_hi][A_lo]
+  uint8_t* const bsm = smem + (size_t)kTcStages * stage_bytes;   // B ring: `bring` x [B_hi][B_lo], filled by TMA
+  const int look = bring - 2;                       // the weight tile of step it + look is requested at step it
 
   if (tid == 0) {
     mbar_init(&bar_empty[0], 1);
     mbar_init(&bar_empty[1], 1);
+    for (int b = 0; b < kTcMaxBRing; ++b) mbar_init(&bar_full[b], 1);
     mbar_init(&bar_done, 1);
     fence_barrier_init();
     kmask_s = 0u;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   tc_fence_before();
@@ -183,7 +206,6 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t idesc = make_idesc_tf32(kTcM, N);
   const int J = c_in / kTcKC;
-  const int nB4 = 4 * N;  // float4 elements of one B chunk
 
   // rulebook columns of this tile for all offsets at once; which offsets have any neighbour in the tile
   {
@@ -224,8 +246,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
   const int g_q = (lane >> 3) & 3;
   const int g_r0 = (lane & 7) + 8 * warp, g_r1 = g_r0 + 64;
 
-  float4 qa0[kTcPrefetch], qa1[kTcPrefetch], qb[kTcPrefetch][NB];
-  auto load_step = [&](int step, float4& a0, float4& a1, float4* b) {
+  float4 qa0[kTcPrefetch], qa1[kTcPrefetch];
+  auto load_step = [&](int step, float4& a0, float4& a1) {
     const int o = step / J, j = step - o * J;
     const int k = klist[off_begin + o];
     const int tk = mirror ? (K - 1 - k) : k;
@@ -234,17 +256,22 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
     a1 = a0;
     if (src0 >= 0) a0 = __ldg((const float4*)(X + (size_t)src0 * c_in + j * kTcKC + g_q * 4));
     if (src1 >= 0) a1 = __ldg((const float4*)(X + (size_t)src1 * c_in + j * kTcKC + g_q * 4));
-    const float4* wsrc = (const float4*)(Wp + ((size_t)k * J + j) * (size_t)N * kTcKC);
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int e = tid + i * kTcThreads;
-      b[i] = (e < nB4) ? __ldg(wsrc + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  };
+  // weight tile of pipeline step `step` -> B ring slot step % bring  (thread 0 only): rows [(k*J + j) * N/2, +N/2) of
+  // the 2-D tensor [K*J*N/2][64 floats] that the prep kernel wrote = the contiguous 128*N-byte [hi | lo] chunk
+  auto request_weights = [&](int step) {
+    const int o = step / J, j = step - o * J;
+    const int k = klist[off_begin + o];
+    const int slot = step % bring;
+    mbar_arrive_expect_tx(&bar_full[slot], 2 * b_bytes);
+    tma_load_2d(bsm + (size_t)slot * 2 * b_bytes, &w_map, 0, (k * J + j) * (N / 2), &bar_full[slot]);
   };
 
 #pragma unroll
   for (int p = 0; p < kTcPrefetch; ++p)
-    if (p < total) load_step(p, qa0[p], qa1[p], qb[p]);
+    if (p < total) load_step(p, qa0[p], qa1[p]);
+  if (tid == 0)
+    for (int p = 0; p < look && p < total; ++p) request_weights(p);
 
   for (int i0 = 0; i0 < total; i0 += kTcPrefetch) {
 #pragma unroll
@@ -257,30 +284,28 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
           mbar_wait(&bar_empty[s], (uint32_t)(((it - kTcStages) >> 1) & 1));
           tc_fence_after();
         }
+        // slot (it + look) % bring held the weights of step it + look - bring = it - 2, whose MMAs have drained
+        if (tid == 0 && it + look < total) request_weights(it + look);
         float4* Ahi = (float4*)st;
         float4* Alo = (float4*)(st + a_bytes);
-        float4* Bhi = (float4*)(st + 2 * a_bytes);
-        float4* Blo = (float4*)(st + 2 * a_bytes + b_bytes);
         split_store(qa0[p], &Ahi[g_q * kTcM + g_r0], &Alo[g_q * kTcM + g_r0]);
         split_store(qa1[p], &Ahi[g_q * kTcM + g_r1], &Alo[g_q * kTcM + g_r1]);
-#pragma unroll
-        for (int i = 0; i < NB; ++i) {
-          const int e = tid + i * kTcThreads;
-          if (e < nB4) split_store(qb[p][i], &Bhi[e], &Blo[e]);
-        }
-        if (it + kTcPrefetch < total) load_step(it + kTcPrefetch, qa0[p], qa1[p], qb[p]);   // refill the queue slot
+        if (it + kTcPrefetch < total) load_step(it + kTcPrefetch, qa0[p], qa1[p]);   // refill the queue slot
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
+          const int slot = it % bring;
+          mbar_wait(&bar_full[slot], (uint32_t)((it / bring) & 1));   // TMA bytes of this step's weight tile landed
           tc_fence_after();
           const uint32_t sa = smem_u32(st);
+          const uint32_t sb = smem_u32(bsm + (size_t)slot * 2 * b_bytes);
           const uint32_t a_lbo = kTcM * 16, b_lbo = (uint32_t)N * 16;
 #pragma unroll
           for (int kk = 0; kk < kTcKC / 8; ++kk) {
             const uint64_t ahi = make_smem_desc(sa + kk * 2 * a_lbo, a_lbo, 128);
             const uint64_t alo = make_smem_desc(sa + a_bytes + kk * 2 * a_lbo, a_lbo, 128);
-            const uint64_t bhi = make_smem_desc(sa + 2 * a_bytes + kk * 2 * b_lbo, b_lbo, 128);
-            const uint64_t blo = make_smem_desc(sa + 2 * a_bytes + b_bytes + kk * 2 * b_lbo, b_lbo, 128);
+            const uint64_t bhi = make_smem_desc(sb + kk * 2 * b_lbo, b_lbo, 128);
+            const uint64_t blo = make_smem_desc(sb + b_bytes + kk * 2 * b_lbo, b_lbo, 128);
             // main products and the two correction products accumulate in SEPARATE tensor-memory tiles: the
             // accumulator add inside the tensor core truncates, so fewer adds into the large sum = less bias
             const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
@@ -335,283 +360,35 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// =============================================================================================
-// TS-mode kernel: A operand (gathered rows) in TENSOR MEMORY, B operand (weights) in shared memory
-// =============================================================================================
-// Why: scripts/micro/mma_bench.cu shows an M = 128 SS-mode tcgen05.mma never costs less than ~97 cycles (the
-// 128 x 32 B A-operand fetch from shared memory is exposed), which makes small-channel layers MMA-issue bound
-// (16 -> 16: 162 MMAs per 128-row tile).  With A in tensor memory the floor is M * N / 256 cycles (8 for N = 16).
-//
-// Roles: 8 producer warps; thread (warp w, lane l) owns tile row r = 32 * (w % 4) + l -- the TMEM lane quarter a
-// warp may touch is fixed by w % 4 -- and half h = w / 4 of every 32-element contraction step.  Per step it
-// gathers its row's 16 channels (64 contiguous bytes), splits them into tf32 hi / lo and writes them with
-// tcgen05.st into the step's TMEM slot; the same threads copy + split the weight chunk of their half into
-// shared memory (K-major interleaved layout).  A ninth warp issues the MMAs and recycles slots via tcgen05.commit.
-constexpr int kTsProducers = 256;
-constexpr int kTsThreads = kTsProducers + 32;
-constexpr int kTsMaxRing = 6;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// NBH = float4 weight elements per producer thread and step: ceil(4 * N / 128); PF = register prefetch depth
-template <int NBH, int PF>
-__global__ void __launch_bounds__(kTsThreads) conv_ts_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
-                                                              const int32_t* __restrict__ nbr, int64_t n_q, int K,
-                                                              int c_in, int c_out, int mirror, uint32_t tmem_cols,
-                                                              uint32_t col_a0, int ring,
-                                                              const int32_t* __restrict__ order,
-                                                              float* __restrict__ Y) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_empty[kTsMaxRing];
-  __shared__ uint64_t bar_done;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int idx_all[kTcMaxK][kTcM];
-  __shared__ int klist[kTcMaxK];
-  __shared__ unsigned kmask_s;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * kTcM;
-  const int N = c_out;
-  const uint32_t bh_bytes = (uint32_t)N * 64;              // one half (16 k-values) of one of B_hi / B_lo
-  const uint32_t stage_bytes = 4 * bh_bytes;               // [hi h0][hi h1][lo h0][lo h1]
-
-  if (tid == 0) {
-    for (int s = 0; s < ring; ++s) mbar_init(&bar_empty[s], 1);
-    mbar_init(&bar_done, 1);
-    fence_barrier_init();
-    kmask_s = 0u;
+static int make_weight_map(CUtensorMap* map, void* base, cuuint64_t rows, uint32_t box_rows) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+      set_error("pgs_conv_fwd_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return PGS_ERR_CUDA;
+    }
+    encode = (EncodeTiledFn)fn;
   }
-  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const int J = c_in / 16;   // halves per offset
-
-  if (tid < kTsProducers) {
-    unsigned mine = 0u;
-    for (int e = tid; e < K * kTcM; e += kTsProducers) {
-      const int k = e / kTcM, r = e - k * kTcM;
-      const int64_t row = row0 + r;
-      int v = -1;
-      if (row < n_q) v = nbr ? __ldg(&nbr[(int64_t)k * n_q + row]) : (int)row;
-      idx_all[k][r] = v;
-      if (v >= 0) mine |= 1u << k;
-    }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) mine |= __shfl_xor_sync(0xffffffffu, mine, sft);
-    if (lane == 0 && mine) atomicOr(&kmask_s, mine);
+  const cuuint64_t gdim[2] = {64, rows};          // innermost first: 64 floats = 256 B per row
+  const cuuint64_t gstride[1] = {256};            // bytes between rows
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("pgs_conv_fwd_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return PGS_ERR_CUDA;
   }
-  __syncthreads();
-  int n_off = 0;
-  {
-    const unsigned km = kmask_s;
-    for (int k = 0; k < K; ++k) {   // weight index order; table offset tk = mirror ? K-1-k : k
-      const int tk = mirror ? (K - 1 - k) : k;
-      if (km & (1u << tk)) {
-        if (tid == 0) klist[n_off] = k;
-        ++n_off;
-      }
-    }
-  }
-  __syncthreads();
-  const int halves = n_off * J;
-  const int total = (halves + 1) >> 1;
-
-  if (warp == kTsProducers / 32) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_tf32(kTcM, N);
-    const uint32_t sbase = smem_u32(smem);
-    const uint32_t b_lbo = (uint32_t)N * 16;
-    int s = 0;
-    for (int it = 0; it < total; ++it) {
-      named_bar_sync(1 + s, kTsThreads);   // producers have filled slot s
-      if (lane == 0) {
-        tc_fence_after();
-        const uint32_t sb = sbase + (uint32_t)s * stage_bytes;
-        const uint32_t ta = tmem_base + col_a0 + (uint32_t)s * 64u;   // [A_hi: 32 columns][A_lo: 32 columns]
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          // K-step kk covers k-values 8kk..8kk+7: half kk / 2, 16-byte chunks 2 * (kk % 2) and + 1
-          const uint32_t boff = (uint32_t)(kk >> 1) * bh_bytes + (uint32_t)(kk & 1) * 2 * b_lbo;
-          const uint64_t bhi = make_smem_desc(sb + boff, b_lbo, 128);
-          const uint64_t blo = make_smem_desc(sb + 2 * bh_bytes + boff, b_lbo, 128);
-          const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
-          umma_tf32_ts(tmem_base, ta + kk * 8, bhi, idesc, first);
-          umma_tf32_ts(tmem_base + (uint32_t)N, ta + 32 + kk * 8, bhi, idesc, first);
-          umma_tf32_ts(tmem_base + (uint32_t)N, ta + kk * 8, blo, idesc, 1u);
-        }
-        umma_commit(&bar_empty[s]);
-      }
-      __syncwarp();
-      if (++s == ring) s = 0;
-    }
-    if (lane == 0) umma_commit(&bar_done);
-  } else {
-    // ===================== producers =====================
-    const int h = warp >> 2;                        // which half of every step this thread feeds
-    const int r = 32 * (warp & 3) + lane;           // tile row == TMEM lane
-    const int ht = tid & 127;                       // index among the 128 threads of my half
-    const int nB4 = 4 * N;                          // float4 elements of one weight half ([q][n][4])
-    const uint32_t lane_addr = ((uint32_t)(32 * (warp & 3)) << 16);
-
-    float4 qa[PF][4], qb[PF][NBH];
-    int po[PF], pj[PF];   // (offset ordinal, 16-channel chunk) of MY half of the step held by each queue slot
-    auto load_half = [&](int o, int j, float4* a, float4* b) {
-      if (o < n_off) {
-        const int k = klist[o];
-        const int tk = mirror ? (K - 1 - k) : k;
-        const int src = idx_all[tk][r];
-        if (src >= 0) {
-          const float4* g = (const float4*)(X + (size_t)src * c_in + j * 16);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = __ldg(g + i);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float4* wsrc = (const float4*)(Wp + ((size_t)k * J + j) * (size_t)N * 16);
-#pragma unroll
-        for (int i = 0; i < NBH; ++i) {
-          const int e = ht + i * 128;
-          b[i] = (e < nB4) ? __ldg(wsrc + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < NBH; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    {
-      int o = 0, j = h;   // my halves are g = h, h + 2, h + 4, ...
-      while (j >= J) {
-        j -= J;
-        ++o;
-      }
-#pragma unroll
-      for (int p = 0; p < PF; ++p) {
-        po[p] = o;
-        pj[p] = j;
-        if (p < total) load_half(o, j, qa[p], qb[p]);
-        j += 2;
-        while (j >= J) {
-          j -= J;
-          ++o;
-        }
-      }
-    }
-    int s = 0;
-    for (int i0 = 0; i0 < total; i0 += PF) {
-#pragma unroll
-      for (int p = 0; p < PF; ++p) {
-        const int it = i0 + p;
-        if (it < total) {
-          if (it >= ring) {   // MMAs of step it - ring must have drained this slot
-            mbar_wait(&bar_empty[s], (uint32_t)(((it / ring) - 1) & 1));
-            tc_fence_after();
-          }
-          // A: 16 channels of my row -> hi / lo -> TMEM columns [16h, 16h+16) of the slot's A_hi / A_lo blocks
-          {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float v[4] = {qa[p][i].x, qa[p][i].y, qa[p][i].z, qa[p][i].w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float hv = to_tf32_rn(v[t]);
-                hi[4 * i + t] = __float_as_uint(hv);
-                lo[4 * i + t] = __float_as_uint(to_tf32_rn(v[t] - hv));
-              }
-            }
-            const uint32_t ta = tmem_base + lane_addr + col_a0 + (uint32_t)s * 64u + (uint32_t)h * 16u;
-            tmem_st16(ta, hi);
-            tmem_st16(ta + 32, lo);
-          }
-          // B: my share of the weight half -> shared memory, K-major interleaved [q][n][4]
-          {
-            uint8_t* st = smem + (size_t)s * stage_bytes + (size_t)h * bh_bytes;
-            float4* Bhi = (float4*)st;
-            float4* Blo = (float4*)(st + 2 * bh_bytes);
-#pragma unroll
-            for (int i = 0; i < NBH; ++i) {
-              const int e = ht + i * 128;
-              if (e < nB4) split_store(qb[p][i], &Bhi[e], &Blo[e]);
-            }
-          }
-          tmem_st_wait();
-          tc_fence_before();
-          fence_proxy_async();
-          named_bar_arrive(1 + s, kTsThreads);
-          if (++s == ring) s = 0;
-          // refill the queue slot with my half of the step PF ahead
-          int o = po[p], j = pj[p] + 2 * PF;
-          while (j >= J) {
-            j -= J;
-            ++o;
-          }
-          po[p] = o;
-          pj[p] = j;
-          if (it + PF < total) load_half(o, j, qa[p], qb[p]);
-        }
-      }
-    }
-    if (total > 0) {
-      mbar_wait(&bar_done, 0);
-      tc_fence_after();
-    }
-    // epilogue: warp w reads TMEM lanes 32*(w%4).., columns of half (w/4); main + correction tiles summed in fp32
-    const int lq = warp & 3, half = warp >> 2;
-    const int64_t rt = row0 + lq * 32 + lane;
-    const bool rr_ok = rt < n_q;
-    const int64_t rr = (rr_ok && order) ? (int64_t)__ldg(&order[rt]) : rt;
-    const int c_begin = half * (N / 2), c_end = c_begin + N / 2;   // N is a multiple of 16
-    for (int c = c_begin; c < c_end; c += 8) {
-      uint32_t v[8], u[8];
-      if (total > 0) {
-        tmem_ld8(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c, v);
-        tmem_ld8(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(N + c), u);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0u;
-      }
-      if (rr_ok) {
-        float4* y = (float4*)(Y + (size_t)rr * c_out + c);
-        y[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-        y[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+  return PGS_OK;
 }
 
 static inline uint32_t tmem_cols_for(int n) {
@@ -631,7 +408,7 @@ int pgs_conv_tc_supported(int32_t c_in, int32_t c_out) {
 }
 
 size_t pgs_conv_tc_scratch_bytes(int32_t K, int32_t c_in, int32_t c_out) {
-  return align_up((size_t)K * c_in * c_out * sizeof(float), 256);
+  return align_up(2 * (size_t)K * c_in * c_out * sizeof(float), 256);   // tf32 hi + lo planes
 }
 
 int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const int32_t* order, int64_t n_q, int32_t K,
@@ -642,66 +419,42 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const in
   PGS_CHECK_ARG(pgs_conv_tc_supported(c_in, c_out), "channel counts not supported by the tcgen05 path");
   PGS_CHECK_ARG(nbr != nullptr || K == 1, "nbr == NULL requires K == 1");
   PGS_CHECK_ARG(scratch_bytes >= pgs_conv_tc_scratch_bytes(K, c_in, c_out), "scratch too small");
+  PGS_CHECK_ARG(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned (TMA source)");
   if (n_q == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   float* Wp = (float*)scratch;
-  const int64_t total = (int64_t)K * c_in * c_out;
+  const int64_t total = 2 * (int64_t)K * c_in * c_out;
   int pg = (int)((total + 255) / 256);
   if (pg > kNumSM * 8) pg = kNumSM * 8;
   if (W != nullptr)   // W == NULL: scratch already holds the arranged weights (pgs_conv_prep_weights_batch)
     conv_tc_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wp);
-  const size_t smem = (size_t)kTcStages * (2 * kTcM * kTcKC * 4 + 2 * (size_t)c_out * kTcKC * 4);
-  const unsigned gx = (unsigned)((n_q + kTcM - 1) / kTcM);
-  static int mode_ts = -1;
-  if (mode_ts < 0) {
-    const char* e = getenv("PGS_CONV_TC_MODE");
-    mode_ts = (e && e[0] == 't') ? 1 : 0;   // "ts" selects the tensor-memory-operand kernel (measured slower)
+  // tensor map of the arranged weights: [K * J * N/2 rows][64 floats], one box = N/2 rows = the 128*N-byte (k, j) chunk
+  CUtensorMap w_map;
+  {
+    const cuuint64_t rows = (cuuint64_t)K * (c_in / kTcKC) * (c_out / 2);
+    int rc = make_weight_map(&w_map, Wp, rows, (uint32_t)(c_out / 2));
+    if (rc != PGS_OK) return rc;
   }
+  // weight ring depth: as deep as fits next to the 32 KB A ring within ~100 KB per CTA (2..4)
+  int bring = kTcMaxBRing;
+  while (bring > 2 && (size_t)kTcStages * 2 * kTcM * kTcKC * 4 + (size_t)bring * 2 * c_out * kTcKC * 4 > 100 * 1024) --bring;
+  const size_t smem = (size_t)kTcStages * 2 * kTcM * kTcKC * 4 + (size_t)bring * 2 * (size_t)c_out * kTcKC * 4;
+  const unsigned gx = (unsigned)((n_q + kTcM - 1) / kTcM);
   static bool attr_set = false;
   if (!attr_set) {
-    PGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    PGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    PGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    PGS_CUDA(cudaFuncSetAttribute(conv_ts_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    PGS_CUDA(cudaFuncSetAttribute(conv_ts_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    PGS_CUDA(cudaFuncSetAttribute(conv_ts_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-    PGS_CUDA(cudaFuncSetAttribute(conv_ts_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+    PGS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
   }
-  if (mode_ts) {
-    // tensor-memory columns: [0, 2N) accumulators (main, correction), then `ring` A slots of 64 columns
-    const uint32_t col_a0 = (uint32_t)((2 * c_out + 63) / 64 * 64);
-    uint32_t cols = tmem_cols_for((int)col_a0 + 3 * 64);
-    if (cols > 512) cols = 512;
-    int ring = (int)((cols - col_a0) / 64);
-    if (ring > kTsMaxRing) ring = kTsMaxRing;
-    while (ring > 2 && (size_t)ring * 4 * c_out * 64 > 160 * 1024) --ring;
-    const size_t sm = (size_t)ring * 4 * c_out * 64;
-    if (c_out <= 32)
-      conv_ts_kernel<1, 4><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
-    else if (c_out <= 64)
-      conv_ts_kernel<2, 3><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
-    else if (c_out <= 128)
-      conv_ts_kernel<4, 2><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
-    else
-      conv_ts_kernel<6, 2><<<gx, kTsThreads, sm, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, col_a0, ring, order, Y);
-  } else {
-    const uint32_t cols = tmem_cols_for(2 * c_out);
-    // few row tiles: spread the kernel offsets of a tile over several CTAs (partial tiles meet in Y by atomicAdd)
-    int ksplit = 1;
-    if (K > 1 && gx * 2 <= (unsigned)kNumSM) {   // (splitting mid-size layers too measured slower: atomics + memset)
-      ksplit = (int)((2 * kNumSM) / gx);
-      if (ksplit > 9) ksplit = 9;
-    }
-    if (ksplit > 1) PGS_CUDA(cudaMemsetAsync(Y, 0, (size_t)n_q * c_out * sizeof(float), s));
-    const dim3 grid(gx, ksplit);
-    if (c_out <= 64)
-      conv_tc_kernel<1><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
-    else if (c_out <= 128)
-      conv_tc_kernel<2><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
-    else
-      conv_tc_kernel<3><<<grid, kTcThreads, smem, s>>>(X, Wp, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, order, Y);
+  const uint32_t cols = tmem_cols_for(2 * c_out);
+  // few row tiles: spread the kernel offsets of a tile over several CTAs (partial tiles meet in Y by atomicAdd)
+  int ksplit = 1;
+  if (K > 1 && gx * 2 <= (unsigned)kNumSM) {   // (splitting mid-size layers too measured slower: atomics + memset)
+    ksplit = (int)((2 * kNumSM) / gx);
+    if (ksplit > 9) ksplit = 9;
   }
+  if (ksplit > 1) PGS_CUDA(cudaMemsetAsync(Y, 0, (size_t)n_q * c_out * sizeof(float), s));
+  const dim3 grid(gx, ksplit);
+  conv_tc_kernel<<<grid, kTcThreads, smem, s>>>(X, w_map, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, bring, order, Y);
   count_launch(W != nullptr ? 2 : 1);
   PGS_CHECK_LAUNCH();
   return PGS_OK;
