@@ -148,6 +148,21 @@ __device__ __forceinline__ double box_box_lb2(const float* qlo, const float* qhi
   return s;
 }
 
+// lower bound of the squared distance from a point to a box (same monotonicity argument as box_box_lb2)
+template <int D>
+__device__ __forceinline__ double point_box_lb2(const double* q, const float* __restrict__ clo,
+                                                const float* __restrict__ chi) {
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double g1 = __dsub_rn((double)clo[d], q[d]);
+    const double g2 = __dsub_rn(q[d], (double)chi[d]);
+    const double g = fmax(fmax(g1, g2), 0.0);
+    s = __dadd_rn(s, __dmul_rn(g, g));
+  }
+  return s;
+}
+
 // candidate block visited at step t of the outward sweep from block qb
 __device__ __forceinline__ int sweep_block(int qb, int t) { return (t & 1) ? qb + ((t + 1) >> 1) : qb - (t >> 1); }
 
@@ -194,10 +209,13 @@ __global__ void __launch_bounds__(kHT) hdb_knn_kernel(const float* __restrict__ 
       const int blk = __shfl_sync(0xffffffffu, cb, src);
       const int64_t p0 = (int64_t)blk * kHB;
       const int cnt = (int)min((int64_t)kHB, n - p0);
+      // per lane: only points whose own k-th distance still reaches the candidate box look at it (see hdb_search_kernel)
+      const bool want = valid && point_box_lb2<D>(q, blo + (int64_t)blk * D, bhi + (int64_t)blk * D) <= kth;
+      if (!__any_sync(0xffffffffu, want)) continue;
       __syncwarp();
       for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
       __syncwarp();
-      if (valid) {
+      if (want) {
         for (int j = 0; j < cnt; ++j) {
           double x = sqdist_rn<D>(q, &s_pts[wib][j * D]);
           if (x < kth) {
@@ -258,6 +276,11 @@ __global__ void __launch_bounds__(kHT) hdb_round_init_kernel(const int32_t* __re
   }
 }
 
+// search statistics of the last pgs_hdb_mst call (diagnostics: pgs_hdb_search_stats): per round
+// {sweep steps, candidate blocks evaluated, point pairs evaluated, warps that ran the full sweep}
+__device__ unsigned long long g_hdb_stats[64 * 4];
+__device__ unsigned long long g_hdb_clk[64 * 4];   // per round: sum / max of warp cycles, sum / max of cycles in point evaluation
+
 __device__ __forceinline__ double u2d(uint64_t u) { return u == kU64Max ? INFINITY : __longlong_as_double((long long)u); }
 
 template <int D>
@@ -265,7 +288,7 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
     const float* __restrict__ P, const int32_t* __restrict__ sids, const double* __restrict__ core_sorted,
     const int32_t* __restrict__ comp, int64_t n, int nb, const float* __restrict__ blo, const float* __restrict__ bhi,
     const double* __restrict__ bmincore, const int32_t* __restrict__ bcomp, double alpha,
-    uint64_t* __restrict__ U, double* __restrict__ bestw, int32_t* __restrict__ bestp) {
+    uint64_t* __restrict__ U, double* __restrict__ bestw, int32_t* __restrict__ bestp, int round) {
   __shared__ float s_pts[kHT / 32][kHB * D];
   __shared__ double s_core[kHT / 32][kHB];
   __shared__ int s_comp[kHT / 32][kHB];
@@ -293,14 +316,23 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
   double bw = INFINITY;  // best weight
   int bj = -1, blo_id = 0x7fffffff, bhi_id = 0x7fffffff;
   double published = INFINITY;
+  unsigned st_steps = 0, st_blocks = 0, st_pairs = 0;
+  double ucache = INFINITY;   // last value read from U[ca]
+  const long long t_begin = clock64();
+  long long t_eval = 0;
 
   const int span = 2 * max(qb, nb - 1 - qb) + 1;
   for (int base = 0; base < span; base += 32) {
-    // pruning bound: my best so far and whatever my component has already published
-    double bnd = valid ? fmin(bw, u2d(*(volatile uint64_t*)&U[ca])) : -1.0;
+    // pruning bound: my best so far and whatever my component has already published.  U[ca] is ONE address per
+    // component: in the late rounds (2..40 components) every warp of the grid polling it at every step serialises on a
+    // few L2 lines (measured: 71 ms per round at 480 k points whatever the real work) -- poll every 8th step; a stale
+    // value is only a weaker (still valid) upper bound.
+    if (((base >> 5) & 7) == 0) ucache = valid ? u2d(*(volatile uint64_t*)&U[ca]) : INFINITY;
+    double bnd = valid ? fmin(bw, ucache) : -1.0;
     if (core_a > bnd) bnd = -1.0;  // nothing at this lane can still win (w >= core_a)
     const double wb = warp_max_d(bnd);
     if (wb < 0.0) break;           // every lane of the block is settled
+    ++st_steps;
     const double wba = wb * alpha;                              // bound on the raw distance (w >= d / alpha)
     const double wb2 = wba * wba * (1.0 + 8.0 * DBL_EPSILON);  // squared-space bound, rounded up
     const int cb = sweep_block(qb, base + lane);
@@ -311,12 +343,24 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
              box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb2;
     }
     unsigned mask = __ballot_sync(0xffffffffu, pass);
+    const long long t_e0 = clock64();
     while (mask) {
       const int src = __ffs(mask) - 1;
       mask &= mask - 1;
       const int blk = __shfl_sync(0xffffffffu, cb, src);
       const int64_t p0 = (int64_t)blk * kHB;
       const int cnt = (int)min((int64_t)kHB, n - p0);
+      // The box-to-box test above uses the LOOSEST bound of the 32 lanes: one lane with a far best candidate (a block
+      // straddling two clusters, an outlier) would drag the whole warp through every block point by point (measured:
+      // a single warp spending 135 M cycles = the entire 71 ms of a late round).  Per lane: point-to-box bound against
+      // the lane's OWN pruning bound; the block is staged only if some lane still wants it.
+      bool want = false;
+      if (bnd >= 0.0 && fmax(core_a, bmincore[blk]) <= bnd) {
+        const double ba = bnd * alpha;
+        want = point_box_lb2<D>(q, blo + (int64_t)blk * D, bhi + (int64_t)blk * D) <= ba * ba * (1.0 + 8.0 * DBL_EPSILON);
+      }
+      if (!__any_sync(0xffffffffu, want)) continue;
+      ++st_blocks;
       __syncwarp();
       for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
       if (lane < cnt) {
@@ -325,11 +369,12 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
         s_oid[wib][lane] = sids[p0 + lane];
       }
       __syncwarp();
-      if (bnd >= 0.0) {
+      if (want) {
         for (int j = 0; j < cnt; ++j) {
           if (s_comp[wib][j] == ca) continue;
           double w = fmax(core_a, s_core[wib][j]);
           if (w > bnd) continue;
+          ++st_pairs;
           const double d2 = sqdist_rn<D>(q, &s_pts[wib][j * D]);
           const double ba = bnd * alpha;
           if (d2 > ba * ba * (1.0 + 8.0 * DBL_EPSILON)) continue;
@@ -348,6 +393,7 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
         }
       }
     }
+    t_eval += clock64() - t_e0;
     if (valid && bw < published) {
       atomicMin((unsigned long long*)&U[ca], (unsigned long long)__double_as_longlong(bw));
       published = bw;
@@ -357,6 +403,22 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
     bestw[a] = bw;
     bestp[a] = bj;
     if (bw < published) atomicMin((unsigned long long*)&U[ca], (unsigned long long)__double_as_longlong(bw));
+  }
+  if (round < 64) {
+    unsigned pr = st_pairs;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, sft);
+    if (lane == 0) {
+      atomicAdd(&g_hdb_stats[round * 4 + 0], (unsigned long long)st_steps);
+      atomicAdd(&g_hdb_stats[round * 4 + 1], (unsigned long long)st_blocks);
+      atomicAdd(&g_hdb_stats[round * 4 + 2], (unsigned long long)pr);
+      atomicAdd(&g_hdb_stats[round * 4 + 3], (unsigned long long)(st_steps * 32 >= (unsigned)(2 * max(qb, nb - 1 - qb) + 1)));
+      const unsigned long long tt = (unsigned long long)(clock64() - t_begin);
+      atomicAdd(&g_hdb_clk[round * 4 + 0], tt);
+      atomicMax(&g_hdb_clk[round * 4 + 1], tt);
+      atomicAdd(&g_hdb_clk[round * 4 + 2], (unsigned long long)t_eval);
+      atomicMax(&g_hdb_clk[round * 4 + 3], (unsigned long long)t_eval);
+    }
   }
 }
 
@@ -520,6 +582,13 @@ static int hdb_mst_impl(const float* X, int64_t n, int k, double alpha, double* 
     return PGS_ERR_RANGE;
   }
   int32_t n_edges = 0, rounds = 0;
+  {
+    void* sp = nullptr;
+    PGS_CUDA(cudaGetSymbolAddress(&sp, g_hdb_stats));
+    PGS_CUDA(cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * 64 * 4, s));
+    PGS_CUDA(cudaGetSymbolAddress(&sp, g_hdb_clk));
+    PGS_CUDA(cudaMemsetAsync(sp, 0, sizeof(unsigned long long) * 64 * 4, s));
+  }
   while (n_edges < n - 1) {
     if (rounds >= 64) {
       set_error("pgs_hdb_mst: Boruvka did not converge (%d of %lld edges)", n_edges, (long long)(n - 1));
@@ -527,7 +596,7 @@ static int hdb_mst_impl(const float* X, int64_t n, int k, double alpha, double* 
     }
     hdb_round_init_kernel<<<blocks_for((int64_t)nb * 32), kHT, 0, s>>>(L.comp, n, nb, L.bcomp, L.U, L.E);
     hdb_search_kernel<D><<<gw, kHT, 0, s>>>(L.P, L.sids, L.core_sorted, L.comp, n, nb, L.blo, L.bhi, L.bmincore,
-                                            L.bcomp, alpha, L.U, L.bestw, L.bestp);
+                                            L.bcomp, alpha, L.U, L.bestw, L.bestp, rounds);
     hdb_select_kernel<<<gp, kHT, 0, s>>>(L.sids, L.comp, L.bestw, L.bestp, n, L.U, L.E);
     hdb_merge_kernel<<<gp, kHT, 0, s>>>(L.comp, L.inv, n, L.U, L.E, L.next, L.edge_uv, L.edge_w, L.n_edges);
     hdb_relabel_kernel<<<gp, kHT, 0, s>>>(L.comp, L.next, n);
@@ -560,6 +629,18 @@ static int hdb_mst_impl(const float* X, int64_t n, int k, double alpha, double* 
 using namespace pgs;
 
 extern "C" {
+
+int pgs_hdb_search_stats(int64_t* out_host, int32_t max_rounds) {
+  unsigned long long h[64 * 4];
+  PGS_CUDA(cudaMemcpyFromSymbol(h, g_hdb_stats, sizeof(h)));
+  const int nr = max_rounds < 64 ? max_rounds : 64;
+  for (int i = 0; i < 4 * nr; ++i) out_host[i] = (int64_t)h[i];
+  if (max_rounds < 0) {   // (negative: also return the cycle counters after the 4 * 64 statistics -- profiling scripts)
+    PGS_CUDA(cudaMemcpyFromSymbol(h, g_hdb_clk, sizeof(h)));
+    for (int i = 0; i < 256; ++i) out_host[i] = (int64_t)h[i];
+  }
+  return PGS_OK;
+}
 
 size_t pgs_hdb_scratch_bytes(int64_t n, int32_t D) { return hdb_layout(n < 1 ? 1 : n, D < 1 ? 1 : D, nullptr).total; }
 
