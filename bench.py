@@ -280,6 +280,7 @@ def run_b200(args):
     # ---- untimed pass: per-launch CUDA events around every conv forward / input-gradient launch ----
     # (per-op Python executor, same kernels and order as the native executor; events would perturb the timed region)
     prof, dw_prof = [], []
+    dp.local_only = True      # the other ranks have left: no collective in these extra steps
     me.PROFILE, me.PROFILE_DW, me.PROFILE_COUNT_PAIRS = prof, dw_prof, True
     prof_steps = 3
     for i in range(prof_steps):

@@ -435,10 +435,22 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const in
     int rc = make_weight_map(&w_map, Wp, rows, (uint32_t)(c_out / 2));
     if (rc != PGS_OK) return rc;
   }
-  // weight ring depth: as deep as fits next to the 32 KB A ring within ~100 KB per CTA (2..4)
+  // weight ring depth (2..4 tiles of 128 * Cout bytes next to the 32 KB A ring): the deepest ring that does not cost a
+  // resident CTA on layers with enough row tiles to need them (a 4-deep ring at Cout = 64 drops 3 -> 2 CTAs per SM and
+  // measured 7 % slower over the step); few-tile layers take the deepest ring that fits 100 KB.
+  const size_t a_ring = (size_t)kTcStages * 2 * kTcM * kTcKC * 4, b_tile = 2 * (size_t)c_out * kTcKC * 4;
+  const size_t static_smem = sizeof(int) * kTcMaxK * kTcM + 1024;
+  auto ctas_per_sm = [&](int ring) {
+    const size_t per = a_ring + (size_t)ring * b_tile + static_smem;
+    size_t c = (size_t)227 * 1024 / per;
+    return (int)(c > 4 ? 4 : c);   // 64 registers x 256 threads: at most 4 CTAs per SM
+  };
+  const unsigned gx0 = (unsigned)((n_q + kTcM - 1) / kTcM);
+  const int needed = (int)((gx0 + kNumSM - 1) / kNumSM);
+  const int target = ctas_per_sm(2) < needed ? ctas_per_sm(2) : needed;
   int bring = kTcMaxBRing;
-  while (bring > 2 && (size_t)kTcStages * 2 * kTcM * kTcKC * 4 + (size_t)bring * 2 * c_out * kTcKC * 4 > 100 * 1024) --bring;
-  const size_t smem = (size_t)kTcStages * 2 * kTcM * kTcKC * 4 + (size_t)bring * 2 * (size_t)c_out * kTcKC * 4;
+  while (bring > 2 && (a_ring + (size_t)bring * b_tile > 100 * 1024 || ctas_per_sm(bring) < target)) --bring;
+  const size_t smem = a_ring + (size_t)bring * b_tile;
   const unsigned gx = (unsigned)((n_q + kTcM - 1) / kTcM);
   static bool attr_set = false;
   if (!attr_set) {

@@ -26,7 +26,10 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        import datetime
+        # a rank that leaves the collective pattern must fail fast, not sit in NCCL's default 10-minute watchdog
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("PGS_DIST_TIMEOUT_S", "180"))))
     return rank, world, local
 
 
@@ -89,9 +92,12 @@ class DataParallelStep:
         model._grad_hook = self._hook
         model._zero_grad_hook = self.bucket.zero   # one memset of the flat buffer instead of one fill per parameter
         self.allreduce_events = None    # set to a list: (start, end) CUDA events around every gradient all-reduce
+        self.local_only = False         # True: skip the collective (a single rank running extra, unmatched steps)
 
     def _hook(self):
         self.bucket.check_views()
+        if self.local_only:
+            return
         ev = self.allreduce_events
         if ev is not None and self.bucket.flat.is_cuda and dist.is_initialized() and dist.get_world_size() > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
