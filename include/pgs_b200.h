@@ -234,6 +234,26 @@ int pgs_nn1_query(const float* spos, const float* qpos, const uint64_t* qkeys, i
                   const int32_t* meta, float cell, int32_t max_ring, int32_t* idx_out, float* d2_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Proposal bookkeeping after clustering  (replaces torch_points_kernels.instance_iou -- reference call sites
+ *     torch_points3d/core/losses/panoptic_losses.py:37,126, every panoptic tracker -- and the dense-mask cross IoU + numpy
+ *     greedy NMS of torch_points3d/models/panoptic/structure_3heads.py:6-17,40-61)
+ * Proposals in CSR form: flat int64 [n_flat] point ids, offs int32 [n_prop + 1].
+ *   pgs_prop_gt_iou   : gt_id int32 [N] = global ground-truth instance of a point (-1 none), gt_size / gt_scene int32
+ *                       [total_gt], prop_scene int32 [n_prop];  inter int32 [n_prop, total_gt] (work), iou fp32 same shape:
+ *                       |P & G| / |P u G| for instances of the proposal's own scene, 0 elsewhere.
+ *   pgs_prop_cross_nms: inter int32 [n_prop, n_prop] receives |P_i & P_j| (i != j); rank_order int32 [n_prop] = proposals in
+ *                       descending score order; keep uint8 [n_prop] = 1 for the proposals greedy NMS picks
+ *                       (a picked proposal removes every later one with cross IoU > threshold).
+ * ------------------------------------------------------------------------------------------ */
+int pgs_prop_gt_iou(const int64_t* flat, const int32_t* offs, int32_t n_prop, int64_t n_flat, const int32_t* gt_id,
+                    int32_t total_gt, const int32_t* gt_size, const int32_t* gt_scene, const int32_t* prop_scene,
+                    int32_t* inter, float* iou, void* stream);
+size_t pgs_prop_nms_scratch_bytes(int64_t n_flat);
+int pgs_prop_cross_nms(const int64_t* flat, const int32_t* offs, int32_t n_prop, int64_t n_flat,
+                       const int32_t* rank_order, float threshold, int32_t* inter, uint8_t* keep, void* scratch,
+                       size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * HDBSCAN  (replaces hdbscan.HDBSCAN(min_cluster_size, min_samples, cluster_selection_epsilon).fit_predict --
  *           un-vendored dependency hdbscan 0.8.27; reference: torch_points3d/utils/hdbscan_cluster.py:8-13,
  *           117-167; models/panoptic/pointgroupembed.py:240-245,704; models/panoptic/pointgroup.py:208-212)

@@ -40,6 +40,11 @@ SIGNATURES = {
     "pgs_bq_export": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "pgs_nn1_query": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_float,
                               c_int32, c_void_p, c_void_p, c_void_p]),
+    "pgs_prop_gt_iou": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "pgs_prop_nms_scratch_bytes": (c_size_t, [c_int64]),
+    "pgs_prop_cross_nms": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
     "pgs_rg_init": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "pgs_rg_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                  c_void_p]),

@@ -74,39 +74,19 @@ class PanopticResults(NamedTuple):
     cluster_type: torch.Tensor
 
     def get_instances(self, nms_threshold=0.3, min_cluster_points=100, min_score=0.5):
-        """Proposal NMS (structure_3heads.py:28-71) through a sparse proposal x point incidence matrix instead
-        of the dense [n_prop, N] mask."""
+        """Proposal NMS (structure_3heads.py:28-71): cross IoU from sorted point -> proposal lists and the greedy loop in
+        one device pass (tpk.proposal_nms -> pgs_prop_cross_nms), then the size / score filters; one read-back of the
+        picked ids (the caller needs a Python list of index tensors)."""
         if not self.clusters:
             return [], []
         if self.cluster_scores is None:
             return None, self.clusters
         dev = self.semantic_logits.device
-        n_prop, n = len(self.clusters), self.semantic_logits.shape[0]
+        keep, order = tpk.proposal_nms(self.clusters, self.cluster_scores, nms_threshold)
         sizes = torch.tensor([c.shape[0] for c in self.clusters], device=dev)
-        pid = torch.repeat_interleave(torch.arange(n_prop, device=dev), sizes)
-        flat = torch.cat(self.clusters)
-        inc = torch.sparse_coo_tensor(torch.stack([pid, flat]), torch.ones(flat.shape[0], device=dev), (n_prop, n))
-        inter = torch.sparse.mm(inc, inc.t()).to_dense()
-        num = sizes.float()
-        cross = inter / (num.unsqueeze(1) + num.unsqueeze(0) - inter)
-        order = torch.argsort(self.cluster_scores, descending=True).tolist()
-        cross = cross.cpu()
-        alive = [True] * n_prop
-        pick = []
-        for i in order:
-            if not alive[i]:
-                continue
-            pick.append(i)
-            sup = (cross[i] > nms_threshold).nonzero().squeeze(1).tolist()
-            for j in sup:
-                alive[j] = False
-        scores = self.cluster_scores.detach().cpu()
-        ids, out = [], []
-        for i in pick:
-            if self.clusters[i].shape[0] > min_cluster_points and scores[i] > min_score:
-                ids.append(i)
-                out.append(self.clusters[i])
-        return ids, out
+        ok = keep & (sizes > min_cluster_points) & (self.cluster_scores.detach() > min_score)
+        ids = order[ok[order]].tolist()                 # picked proposals in descending-score order, like the reference
+        return ids, [self.clusters[i] for i in ids]
 
 
 # --------------------------------------------------------------------------------------------

@@ -169,36 +169,64 @@ def region_grow(pos, labels, batch, ignore_labels=[], nsample=300, radius=0.03, 
     return list(torch.split(members, counts.tolist()))
 
 
+def _csr(instance_idx, dev):
+    """List of index tensors -> (flat int64, offs int32 [n + 1]) on `dev`."""
+    sizes = [int(c.shape[0]) for c in instance_idx]
+    offs = torch.zeros(len(sizes) + 1, dtype=torch.int32)
+    if sizes:
+        offs[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0).to(torch.int32)
+    flat = torch.cat([c.reshape(-1) for c in instance_idx]).to(device=dev, dtype=torch.int64) if sizes else \
+        torch.zeros(0, dtype=torch.int64, device=dev)
+    return flat.contiguous(), offs.to(dev), sizes
+
+
 def instance_iou(instance_idx: List[torch.Tensor], instance_labels: torch.Tensor, batch=None) -> torch.Tensor:
     """IoU of every proposal against every ground-truth instance (tpk signature; reference call sites:
     torch_points3d/core/losses/panoptic_losses.py:37, every panoptic tracker).
     instance_labels: 0 = no instance, 1..M per scene.  -> f32 [n_proposals, sum_s M_s], scenes in order.
-    Tensor-op formulation (the CUDA kernel for this row is SURVEY 8f #3, "next")."""
+    Counting and division run in csrc/proposals.cu (pgs_prop_gt_iou); the label bookkeeping (instances per scene, their
+    sizes) is a handful of reductions over the label vector."""
+    lib = _lib.load()
     dev = instance_labels.device
+    if not instance_labels.is_cuda:
+        raise _lib.PgsError("instance_iou needs CUDA tensors (no CPU path)")
     if batch is None:
         batch = torch.zeros_like(instance_labels)
     n_prop = len(instance_idx)
     nb = int(batch.max()) + 1 if batch.numel() else 0
     per_scene = torch.zeros(nb, dtype=torch.long, device=dev).scatter_reduce(
         0, batch, instance_labels, reduce="amax", include_self=True) if nb else torch.zeros(0, dtype=torch.long, device=dev)
-    offs = torch.cumsum(per_scene, 0) - per_scene
+    offs_gt = torch.cumsum(per_scene, 0) - per_scene
     total = int(per_scene.sum()) if nb else 0
     ious = torch.zeros((n_prop, total), dtype=torch.float32, device=dev)
     if n_prop == 0 or total == 0:
         return ious
-    gid = torch.where(instance_labels > 0, offs[batch] + instance_labels - 1, torch.full_like(instance_labels, -1))
-    gt_size = torch.bincount(gid[gid >= 0], minlength=total).float()
-    sizes = torch.tensor([c.shape[0] for c in instance_idx], device=dev)
-    flat = torch.cat(instance_idx)
-    pid = torch.repeat_interleave(torch.arange(n_prop, device=dev), sizes)
-    g = gid[flat]
-    ok = g >= 0
-    inter = torch.zeros(n_prop * total, dtype=torch.float32, device=dev)
-    inter.index_add_(0, pid[ok] * total + g[ok], torch.ones(int(ok.sum()), device=dev))
-    inter = inter.view(n_prop, total)
-    # a proposal only competes with the instances of its own scene
-    scene_of_prop = batch[torch.stack([c[0] for c in instance_idx])]
-    scene_of_gt = torch.repeat_interleave(torch.arange(nb, device=dev), per_scene)
-    same = scene_of_prop.unsqueeze(1) == scene_of_gt.unsqueeze(0)
-    union = sizes.float().unsqueeze(1) + gt_size.unsqueeze(0) - inter
-    return torch.where(same, inter / union, torch.zeros_like(inter))
+    gid = torch.where(instance_labels > 0, offs_gt[batch] + instance_labels - 1, torch.full_like(instance_labels, -1))
+    gt_size = torch.bincount(gid[gid >= 0], minlength=total).to(torch.int32)
+    gt_scene = torch.repeat_interleave(torch.arange(nb, device=dev), per_scene).to(torch.int32)
+    flat, offs, sizes = _csr(instance_idx, dev)
+    if min(sizes) == 0:
+        raise ValueError("empty proposal")
+    prop_scene = batch[flat[offs[:-1].long()]].to(torch.int32)
+    inter = torch.empty((n_prop, total), dtype=torch.int32, device=dev)
+    check(lib.pgs_prop_gt_iou(ptr(flat), ptr(offs), n_prop, flat.shape[0], ptr(gid.to(torch.int32).contiguous()), total,
+                              ptr(gt_size), ptr(gt_scene), ptr(prop_scene.contiguous()), ptr(inter), ptr(ious), stream_ptr()))
+    return ious
+
+
+def proposal_nms(instance_idx: List[torch.Tensor], scores: torch.Tensor, threshold: float):
+    """Greedy non-maximum suppression over proposals by cross IoU in descending score order
+    (models/panoptic/structure_3heads.py:6-17,40-61) -> (keep bool [n_prop], order int64 [n_prop] = proposals by descending
+    score).  Intersections are counted from the point -> proposals lists (sorted CSR), not from dense masks."""
+    lib = _lib.load()
+    dev = scores.device
+    n_prop = len(instance_idx)
+    flat, offs, sizes = _csr(instance_idx, dev)
+    order = torch.argsort(scores.detach().float(), descending=True, stable=True)
+    inter = torch.empty((n_prop, n_prop), dtype=torch.int32, device=dev)
+    keep = torch.empty(n_prop, dtype=torch.uint8, device=dev)
+    nb = lib.pgs_prop_nms_scratch_bytes(flat.shape[0])
+    scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+    check(lib.pgs_prop_cross_nms(ptr(flat), ptr(offs), n_prop, flat.shape[0], ptr(order.to(torch.int32).contiguous()),
+                                 float(threshold), ptr(inter), ptr(keep), ptr(scratch), nb, stream_ptr()))
+    return keep.bool(), order
