@@ -87,10 +87,8 @@ __global__ void __launch_bounds__(1024) prop_nms_kernel(const int32_t* __restric
         const float iou = (float)it / (float)(ni + (offs[j + 1] - offs[j]) - it);
         if (iou > threshold) alive[j] = 0;
       }
-      if (threadIdx.x == 0) {
-        keep[i] = 1;
-        alive[i] = 0;
-      }
+      if (threadIdx.x == 0) keep[i] = 1;   // (alive[i] stays set: rank r is never visited again, and clearing it here
+                                           //  would race with the other threads' read of the flag above)
     }
     __syncthreads();
   }
