@@ -85,30 +85,33 @@ class Program:
     """Static tape of a MinkowskiUnet / MinkowskiEncoder (built once per model)."""
 
     def __init__(self, net):
-        from . import backbone as B
-        self._B = B
         self.ops = []       # (kind, a, b, dst, index into convs / bns, relu)
         self.convs = []
         self.bns = []
         self.n_slots = 1    # slot 0 = network input
         x = 0
-        if isinstance(net, B.MinkowskiUnet):
+        # duck-typed on purpose: the same tape serves backbone.py's mirror classes AND the reference's own
+        # MinkowskiUnet / MinkowskiEncoder (applications/minkowski.py:129-196) built from its own ResNetDown / ResNetUp /
+        # ResBlock (modules/MinkowskiEngine/api_modules.py) over me.py -- see bind.install(fuse_unet=True)
+        downs = getattr(net, "down_modules", None)
+        ups = getattr(net, "up_modules", None)
+        if downs is None or len(downs) == 0:
+            raise Unsupported("no down_modules")
+        if ups is not None and len(ups) > 0:
             stack = []
-            for i in range(len(net.down_modules) - 1):
-                x = self._resnet(net.down_modules[i], x)
+            for i in range(len(downs) - 1):
+                x = self._resnet(downs[i], x)
                 stack.append(x)
-            x = self._resnet(net.down_modules[-1], x)
+            x = self._resnet(downs[-1], x)
             stack.append(None)
-            for m in net.up_modules:
+            for m in ups:
                 skip = stack.pop()
                 if skip is not None:
                     x = self._emit(OP_CAT, x, skip)
                 x = self._resnet(m, x)
-        elif isinstance(net, B.MinkowskiEncoder):
-            for m in net.down_modules:
-                x = self._resnet(m, x)
         else:
-            raise Unsupported("not a MinkowskiUnet / MinkowskiEncoder")
+            for m in downs:
+                x = self._resnet(m, x)
         self.out_slot = x
         self.params = ([c.kernel for c in self.convs] + [b.bn.weight for b in self.bns] + [b.bn.bias for b in self.bns])
         self.consumers = [0] * self.n_slots
@@ -165,12 +168,11 @@ class Program:
         return self._bn(mods[1], self._conv(mods[0], src), relu)
 
     def _resnet(self, m, src):
-        B = self._B
-        if type(m) not in (B.ResNetDown, B.ResNetUp):
+        if not (hasattr(m, "conv_in") and hasattr(m, "blocks")) or type(m).__name__ not in ("ResNetDown", "ResNetUp"):
             raise Unsupported("module %r" % type(m))
         y = self._conv_bn(m.conv_in, src)
         for blk in (m.blocks if m.blocks is not None else ()):
-            if type(blk) is not B.ResBlock:
+            if type(blk).__name__ != "ResBlock" or not hasattr(blk, "block") or not hasattr(blk, "downsample"):
                 raise Unsupported("block %r" % type(blk))
             mods = list(blk.block)
             if len(mods) != 6 or type(mods[2]) is not ME.MinkowskiReLU or type(mods[5]) is not ME.MinkowskiReLU:

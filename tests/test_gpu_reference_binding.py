@@ -38,12 +38,16 @@ def _scenes(kind, n, grid, radius, count, seed0):
     return scenes.collate([scenes.make_scene(kind, n, grid, radius, seed=seed0 + i) for i in range(count)])
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("which", ["two_level", "paper"])
-def test_reference_unet_runs_on_the_kernels(cuda_device, which):
-    """The reference's MinkowskiUnet (its own forward, skip stack and blocks) over me.py == the package's fused executor
-    with the same state_dict (same kernels: 2e-5), == the CPU oracle (1e-4); parameter gradients agree."""
-    from torch_points3d.applications.minkowski import Minkowski
-    from panopticsegforlargescalepointcloud_b200 import backbone as bb, _lib
+def test_reference_unet_runs_on_the_kernels(cuda_device, which, fused, monkeypatch):
+    """The reference's MinkowskiUnet over me.py -- fused=False: its own forward loop, skip stack and blocks, module by
+    module; fused=True: the same object through bind.install(fuse_unet=True), i.e. the tape compiled from ITS module tree
+    and walked by pgs_unet_forward / pgs_unet_backward -- == the package's mirror with the same state_dict (same kernels:
+    2e-5), == the CPU oracle (1e-4); parameter gradients agree."""
+    from torch_points3d.applications.minkowski import Minkowski, MinkowskiUnet
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb, _lib, fastpath
+    assert getattr(MinkowskiUnet.forward, "_pgs_fused", False)       # bind.install() wrapped the reference class
     cfg = bb.two_level_config(16) if which == "two_level" else bb.paper_backbone_config(16)
     torch.manual_seed(3)
     ref = Minkowski("unet", input_nc=4, num_layers=4, config=rb.config(cfg)).to(cuda_device)
@@ -51,9 +55,13 @@ def test_reference_unet_runs_on_the_kernels(cuda_device, which):
     mine.load_state_dict(ref.state_dict())
     ref.eval(); mine.eval()
     b = _scenes("urban", 9000, 0.2, 5.0, 2, 40)
+    assert type(ref).__module__ == "torch_points3d.applications.minkowski" and fastpath.program_for(ref) is not None
     before = _lib.launch_count()
+    monkeypatch.setattr(fastpath, "ENABLED", fused)
     out_ref = ref(_data(b, cuda_device, ("pos", "coords", "x", "batch")))
+    monkeypatch.setattr(fastpath, "ENABLED", True)
     assert _lib.launch_count() > before                              # the reference's modules launched OUR kernels
+    assert (out_ref.x.grad_fn is not None) and (("UNetFn" in type(out_ref.x.grad_fn).__name__) == fused)
     out_mine = mine(_data(b, cuda_device, ("pos", "coords", "x", "batch")))
     scale = max(1.0, float(out_mine.x.abs().max()))
     assert float((out_ref.x - out_mine.x).abs().max()) <= 2e-5 * scale
