@@ -205,9 +205,32 @@ def run_b200(args):
         def __getitem__(self, k):
             return self.__dict__[k]
 
+    # e2e arm: the batch of step i + 1 is copied from pinned host memory on a second stream while step i computes (what a
+    # data loader with pin_memory + non_blocking does); every step still pays its own host->device copy inside the timed
+    # region, the copy engine just runs beside the SMs.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [{k: torch.empty_like(v, device=dev) for k, v in h.items()} for h in host]   # one device buffer set per pool slot
+    inflight = {}
+
+    def upload(i):
+        d = staging[i % SCENE_POOL]
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))     # the slot's previous consumer (SCENE_POOL steps ago) is done
+        with torch.cuda.stream(copy_stream):
+            for k, v in host[i % SCENE_POOL].items():
+                d[k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        inflight[i] = (d, ev)
+
     def step(i, e2e):
-        src = host[i % SCENE_POOL] if e2e else resident[i % SCENE_POOL]
-        d = {k: v.to(dev, non_blocking=True) for k, v in src.items()} if e2e else src
+        if e2e:
+            if i not in inflight:
+                upload(i)
+            d, ev = inflight.pop(i)
+            torch.cuda.current_stream(dev).wait_event(ev)
+            upload(i + 1)
+        else:
+            d = resident[i % SCENE_POOL]
         dp.step(View(d), epoch=1, step=i, batch_size=spr)
         clusters = tpk.region_grow(d["syn_shifted"], d["syn_pred"], d["batch"], ignore_labels=ignore, nsample=200,
                                    radius=1.5 * GRID, min_cluster_size=10)
@@ -234,7 +257,9 @@ def run_b200(args):
         ar_us = float(np.mean([a.elapsed_time(b) for a, b in dp.allreduce_events])) * 1e3
     dp.allreduce_events = None
     # ---- timed region 2: end to end (pinned host buffers in, loss + partition out) ----
+    inflight.clear()
     ms_e2e, last_e2e, _ = _timed_loop(step, args.steps, True, world, dev)
+    inflight.clear()
     d2h_bytes = 4 + (last_e2e[1].numel() * 8 + len(last_e2e[2]) * 8)
 
     # ---- secondary: latency mode, ONE cylinder per GPU and step (round 1's headline definition) ----

@@ -146,6 +146,6 @@ def test_backward_after_another_forward_rearranges_its_weights(cuda_device):
 
     clean, out0 = grads(False)
     mixed, out1 = grads(True)
-    assert torch.equal(out0, out1)
+    assert float((out0 - out1).abs().max()) <= 2e-5 * max(1.0, float(out0.abs().max()))   # (few-row layers sum by atomicAdd)
     worst = max(float((x - y).norm() / y.norm().clamp_min(1e-12)) for x, y in zip(mixed, clean))
     assert worst <= 1e-3, worst       # (atomic-add ordering only; stale or foreign weight layouts give O(1))
