@@ -90,6 +90,30 @@ class KernelMap:
         return self._pairs
 
 
+def build_coordinate_map(coords, ts_out):
+    """pgs_cmap_build on int32 [n, 4] (batch, x, y, z) rows -> (CoordinateMap of floor(c / ts_out) * ts_out with rows in
+    first-occurrence order, in2out int32 [n]).  Also the voxel de-duplication of transforms.GridSampling3D."""
+    lib = _lib.load()
+    n = coords.shape[0]
+    dev = coords.device
+    cap = lib.pgs_cmap_capacity(n)
+    tkeys = torch.empty(cap, dtype=torch.int64, device=dev)
+    tvals = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_coords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    in2out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    meta = torch.zeros(2, dtype=torch.int32, device=dev)  # [n_out, status]
+    nb = lib.pgs_cmap_build_scratch_bytes(n)
+    scratch = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+    check(lib.pgs_cmap_build(ptr(coords), n, ts_out, ptr(tkeys), ptr(tvals), cap, ptr(out_coords),
+                             ptr(in2out), ptr(meta[0:1]), ptr(meta[1:2]), ptr(scratch), nb, stream_ptr()))
+    n_out, status = meta.tolist()
+    if status & 1:
+        raise ValueError("coordinate outside the supported range (batch < 65536, |xyz| < 32768)")
+    if status & 2:
+        raise _lib.PgsError("coordinate hash table overflow")
+    return CoordinateMap(out_coords[:n_out], n_out, tkeys, tvals, cap, ts_out), in2out[:n]
+
+
 class CoordinateManager:
     """Owns the coordinate maps (one per tensor stride) and kernel maps of one batch."""
 
@@ -112,25 +136,7 @@ class CoordinateManager:
         self.maps[1] = m
 
     def _build(self, coords, ts_out):
-        lib = _lib.load()
-        n = coords.shape[0]
-        dev = coords.device
-        cap = lib.pgs_cmap_capacity(n)
-        tkeys = torch.empty(cap, dtype=torch.int64, device=dev)
-        tvals = torch.empty(cap, dtype=torch.int32, device=dev)
-        out_coords = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
-        in2out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        meta = torch.zeros(2, dtype=torch.int32, device=dev)  # [n_out, status]
-        nb = lib.pgs_cmap_build_scratch_bytes(n)
-        scratch = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
-        check(lib.pgs_cmap_build(ptr(coords), n, ts_out, ptr(tkeys), ptr(tvals), cap, ptr(out_coords),
-                                 ptr(in2out), ptr(meta[0:1]), ptr(meta[1:2]), ptr(scratch), nb, stream_ptr()))
-        n_out, status = meta.tolist()
-        if status & 1:
-            raise ValueError("coordinate outside the supported range (batch < 65536, |xyz| < 32768)")
-        if status & 2:
-            raise _lib.PgsError("coordinate hash table overflow")
-        return CoordinateMap(out_coords[:n_out], n_out, tkeys, tvals, cap, ts_out), in2out[:n]
+        return build_coordinate_map(coords, ts_out)
 
     def get_map(self, ts: int) -> CoordinateMap:
         return self.maps[ts]

@@ -15,8 +15,9 @@ torch_geometric consecutive_cluster, sklearn KDTree.query_radius).  Here every p
   CylinderSampling: rows with (x - cx)^2 + (y - cy)^2 <= r^2 in ascending row order (KDTree.query_radius returns an
                    unordered set; every consumer is order-free), optional re-centring of x, y.
 
-The sort is CUB's radix sort through torch.unique (library code for a plain sort); there is no CPU path: CPU tensors
-raise.  Semantics of the un-vendored torch_cluster / torch_geometric pieces are restated from memory (SURVEY App. B note):
+Voxel de-duplication uses the hot path's own coordinate hash (csrc/cmap.cu, pgs_cmap_build); the remaining sort over the
+occupied voxels (torch.argsort: library radix sort) only establishes the reference's output order.  There is no CPU path:
+CPU tensors raise.  Semantics of the un-vendored torch_cluster / torch_geometric pieces are restated from memory (SURVEY App. B note):
 PARITY UNPINNED against those packages; pinned against oracle/transforms_ref.py, which is checked against an independent
 dictionary-based definition.
 """
@@ -61,14 +62,38 @@ def voxel_ids(coords, batch=None):
 
 def grid_sample_indices(pos, size, batch=None):
     """-> (unique_pos_indices int64 [M] in ascending voxel-id order, cluster int64 [N] consecutive voxel ids,
-    coords float [N, 3] = round(pos / size))."""
+    coords float [N, 3] = round(pos / size)).
+
+    De-duplication runs on the coordinate-hash kernel of the hot path (pgs_cmap_build: one atomicCAS insert per point,
+    first-occurrence voxel numbers), so only the M occupied voxels -- not the N points -- go through a sort, which is
+    there for the ORDER contract alone (consecutive_cluster numbers voxels by ascending linear index).  Grids wider than
+    65535 cells per axis (7.8 km at 0.12 m) fall back to sorting the N linear indices."""
     _need_cuda(pos, "pos")
     coords = torch.round(pos / size)
-    vid = voxel_ids(coords, batch)
-    uniq, cluster = torch.unique(vid, sorted=True, return_inverse=True)
     n = pos.shape[0]
-    last = torch.full((uniq.shape[0],), -1, dtype=torch.int64, device=pos.device)
-    last.scatter_reduce_(0, cluster, torch.arange(n, device=pos.device), reduce="amax", include_self=True)
+    dev = pos.device
+    ci = coords.to(torch.int64)
+    lo, hi = ci.min(0).values, ci.max(0).values
+    nb = (int(batch.max()) + 1) if batch is not None else 1
+    ar = torch.arange(n, device=dev)
+    if n > 0 and int((hi - lo).max()) < 65535 and nb < 65536:
+        from . import me
+        c4 = torch.cat([(batch.to(torch.int64) if batch is not None else torch.zeros(n, dtype=torch.int64, device=dev))
+                        .unsqueeze(1), ci - lo - 32767], 1).to(torch.int32).contiguous()
+        m, in2out = me.build_coordinate_map(c4, 1)
+        first = in2out.long()                                            # voxel number by first occurrence
+        vid = voxel_ids(m.coords[:, 1:4], m.coords[:, 0] if batch is not None else None)   # same offsets: min is shared
+        order = torch.argsort(vid)                                       # M keys
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(order.shape[0], device=dev)
+        cluster = rank[first]
+        n_vox = order.shape[0]
+    else:
+        vid = voxel_ids(coords, batch)
+        uniq, cluster = torch.unique(vid, sorted=True, return_inverse=True)
+        n_vox = uniq.shape[0]
+    last = torch.full((n_vox,), -1, dtype=torch.int64, device=dev)
+    last.scatter_reduce_(0, cluster, ar, reduce="amax", include_self=True)
     return last, cluster, coords
 
 
