@@ -69,7 +69,9 @@ def grid_sample_indices(pos, size, batch=None):
     there for the ORDER contract alone (consecutive_cluster numbers voxels by ascending linear index).  Grids wider than
     65535 cells per axis (7.8 km at 0.12 m) fall back to sorting the N linear indices."""
     _need_cuda(pos, "pos")
-    coords = torch.round(pos / size)
+    # the reference divides on the CPU (grid_transform.py:185, true fp32 division); torch's CUDA kernel turns `tensor / python
+    # scalar` into a multiplication by the reciprocal, which rounds differently near .5 -- divide by a device scalar instead
+    coords = torch.round(pos / torch.full((), float(size), dtype=pos.dtype, device=pos.device))
     n = pos.shape[0]
     dev = pos.device
     ci = coords.to(torch.int64)
