@@ -270,8 +270,8 @@ int pgs_prop_cross_nms(const int64_t* flat, const int32_t* offs, int32_t n_prop,
  * All pointers of this function are HOST pointers.
  * ------------------------------------------------------------------------------------------ */
 size_t pgs_hdb_scratch_bytes(int64_t n, int32_t D);
-/* diagnostics of the last pgs_hdb_mst call: out_host int64 [max_rounds][4] = per Boruvka round {sweep steps (32 leaf boxes
- * each), candidate blocks evaluated point by point, point pairs whose distance was computed, warps that swept every block} */
+/* diagnostics of the last pgs_hdb_mst call: out_host int64 [max_rounds][4] = per Boruvka round {box-test steps (32 group or
+ * leaf boxes each), candidate blocks evaluated point by point, point pairs whose distance was computed, warps} */
 int pgs_hdb_search_stats(int64_t* out_host, int32_t max_rounds);
 int pgs_hdb_mst(const float* X, int64_t n, int32_t D, int32_t min_samples, double alpha,
                 double* core, int32_t* u, int32_t* v, double* w, int32_t* rounds_host,

@@ -26,6 +26,7 @@ namespace pgs {
 
 constexpr int kHB = 32;        // points per leaf block
 constexpr int kHT = 256;       // threads per CTA (8 warps)
+constexpr int kHdbParLanes = 6;   // <= this many interested query lanes: candidates are evaluated lane-parallel
 constexpr uint64_t kU64Max = ~0ull;
 
 __device__ __forceinline__ unsigned f2ord(float f) {
@@ -114,6 +115,59 @@ __global__ void __launch_bounds__(kHT) hdb_block_box_kernel(const float* __restr
   }
 }
 
+// Second level of the box hierarchy: one box per GROUP of 32 consecutive leaf blocks (1024 Morton-consecutive points).
+// The sweeps test a group box first and only look at the 32 leaf boxes of groups that survive: ~nb/32 + survivors steps
+// per warp instead of nb/32 steps of 32 leaf tests each (measured at 480 k points: every warp walked all 15 k leaf boxes
+// in every round, 10.7 M box steps of ~1.5 k cycles).
+template <int D>
+__global__ void __launch_bounds__(kHT) hdb_group_box_kernel(const float* __restrict__ blo, const float* __restrict__ bhi,
+                                                             int nb, int ng, float* __restrict__ glo,
+                                                             float* __restrict__ ghi) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (g >= ng) return;
+  const int b = g * 32 + lane;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    if (b < nb) {
+      lo = blo[(int64_t)b * D + d];
+      hi = bhi[(int64_t)b * D + d];
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if (lane == 0) {
+      glo[(int64_t)g * D + d] = lo;
+      ghi[(int64_t)g * D + d] = hi;
+    }
+  }
+}
+
+// per group: minimum core distance (once) and, per round, the component shared by ALL its blocks (-1: mixed)
+__global__ void __launch_bounds__(kHT) hdb_group_meta_kernel(const double* __restrict__ bmincore,
+                                                              const int32_t* __restrict__ bcomp, int nb, int ng,
+                                                              double* __restrict__ gmincore, int32_t* __restrict__ gcomp) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (g >= ng) return;
+  const int b = g * 32 + lane;
+  if (gmincore) {
+    double c = b < nb ? bmincore[b] : INFINITY;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c = fmin(c, __shfl_xor_sync(0xffffffffu, c, s));
+    if (lane == 0) gmincore[g] = c;
+  }
+  if (gcomp) {
+    const int c = b < nb ? bcomp[b] : -2;           // -2: past the end (neutral), -1: the block itself is mixed
+    const int c0 = __shfl_sync(0xffffffffu, c, 0);
+    const bool uni = __all_sync(0xffffffffu, (c == c0 && c >= 0) || c == -2);
+    if (lane == 0) gcomp[g] = (uni && c0 >= 0) ? c0 : -1;
+  }
+}
+
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
@@ -172,7 +226,8 @@ __device__ __forceinline__ int sweep_block(int qb, int t) { return (t & 1) ? qb 
 template <int D, int KMAX>
 __global__ void __launch_bounds__(kHT) hdb_knn_kernel(const float* __restrict__ P, const int32_t* __restrict__ sids,
                                                        int64_t n, int nb, const float* __restrict__ blo,
-                                                       const float* __restrict__ bhi, int k,
+                                                       const float* __restrict__ bhi, const float* __restrict__ glo,
+                                                       const float* __restrict__ ghi, int k,
                                                        double* __restrict__ core_sorted,
                                                        double* __restrict__ core_orig) {
   __shared__ float s_pts[kHT / 32][kHB * D];
@@ -197,42 +252,52 @@ __global__ void __launch_bounds__(kHT) hdb_knn_kernel(const float* __restrict__ 
   double kth = valid ? INFINITY : -1.0;
   double wb = INFINITY;
 
-  const int span = 2 * max(qb, nb - 1 - qb) + 1;
-  for (int base = 0; base < span; base += 32) {
-    const int cb = sweep_block(qb, base + lane);
-    bool pass = cb >= 0 && cb < nb;
-    if (pass) pass = box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb;
-    unsigned mask = __ballot_sync(0xffffffffu, pass);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int blk = __shfl_sync(0xffffffffu, cb, src);
-      const int64_t p0 = (int64_t)blk * kHB;
-      const int cnt = (int)min((int64_t)kHB, n - p0);
-      // per lane: only points whose own k-th distance still reaches the candidate box look at it (see hdb_search_kernel)
-      const bool want = valid && point_box_lb2<D>(q, blo + (int64_t)blk * D, bhi + (int64_t)blk * D) <= kth;
-      if (!__any_sync(0xffffffffu, want)) continue;
-      __syncwarp();
-      for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
-      __syncwarp();
-      if (want) {
-        for (int j = 0; j < cnt; ++j) {
-          double x = sqdist_rn<D>(q, &s_pts[wib][j * D]);
-          if (x < kth) {
+  const int qg = qb >> 5, ng = (nb + 31) >> 5;
+  const int gspan = 2 * max(qg, ng - 1 - qg) + 1;
+  for (int gbase = 0; gbase < gspan; gbase += 32) {
+    const int cg = sweep_block(qg, gbase + lane);
+    bool gpass = cg >= 0 && cg < ng;
+    if (gpass) gpass = box_box_lb2<D>(qlo, qhi, glo + (int64_t)cg * D, ghi + (int64_t)cg * D) <= wb;
+    unsigned gmask = __ballot_sync(0xffffffffu, gpass);
+    while (gmask) {
+      const int gsrc = __ffs(gmask) - 1;
+      gmask &= gmask - 1;
+      const int grp = __shfl_sync(0xffffffffu, cg, gsrc);
+      const int cb = grp * 32 + lane;
+      bool pass = cb < nb;
+      if (pass) pass = box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb;
+      unsigned mask = __ballot_sync(0xffffffffu, pass);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int blk = __shfl_sync(0xffffffffu, cb, src);
+        const int64_t p0 = (int64_t)blk * kHB;
+        const int cnt = (int)min((int64_t)kHB, n - p0);
+        // per lane: only points whose own k-th distance still reaches the candidate box look at it (see hdb_search_kernel)
+        const bool want = valid && point_box_lb2<D>(q, blo + (int64_t)blk * D, bhi + (int64_t)blk * D) <= kth;
+        if (!__any_sync(0xffffffffu, want)) continue;
+        __syncwarp();
+        for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
+        __syncwarp();
+        if (want) {
+          for (int j = 0; j < cnt; ++j) {
+            double x = sqdist_rn<D>(q, &s_pts[wib][j * D]);
+            if (x < kth) {
 #pragma unroll
-            for (int m = 0; m < KMAX; ++m)
-              if (m < k && x < best[m]) {
-                const double t = best[m];
-                best[m] = x;
-                x = t;
-              }
+              for (int m = 0; m < KMAX; ++m)
+                if (m < k && x < best[m]) {
+                  const double t = best[m];
+                  best[m] = x;
+                  x = t;
+                }
 #pragma unroll
-            for (int m = 0; m < KMAX; ++m)
-              if (m == k - 1) kth = best[m];
+              for (int m = 0; m < KMAX; ++m)
+                if (m == k - 1) kth = best[m];
+            }
           }
         }
+        wb = warp_max_d(kth);
       }
-      wb = warp_max_d(kth);
     }
   }
   if (valid) {
@@ -277,7 +342,7 @@ __global__ void __launch_bounds__(kHT) hdb_round_init_kernel(const int32_t* __re
 }
 
 // search statistics of the last pgs_hdb_mst call (diagnostics: pgs_hdb_search_stats): per round
-// {sweep steps, candidate blocks evaluated, point pairs evaluated, warps that ran the full sweep}
+// {box-test steps (group + leaf level), candidate blocks evaluated, point pairs evaluated, warps}
 __device__ unsigned long long g_hdb_stats[64 * 4];
 __device__ unsigned long long g_hdb_clk[64 * 4];   // per round: sum / max of warp cycles, sum / max of cycles in point evaluation
 
@@ -287,7 +352,8 @@ template <int D>
 __global__ void __launch_bounds__(kHT) hdb_search_kernel(
     const float* __restrict__ P, const int32_t* __restrict__ sids, const double* __restrict__ core_sorted,
     const int32_t* __restrict__ comp, int64_t n, int nb, const float* __restrict__ blo, const float* __restrict__ bhi,
-    const double* __restrict__ bmincore, const int32_t* __restrict__ bcomp, double alpha,
+    const double* __restrict__ bmincore, const int32_t* __restrict__ bcomp, const float* __restrict__ glo,
+    const float* __restrict__ ghi, const double* __restrict__ gmincore, const int32_t* __restrict__ gcomp, double alpha,
     uint64_t* __restrict__ U, double* __restrict__ bestw, int32_t* __restrict__ bestp, int round) {
   __shared__ float s_pts[kHT / 32][kHB * D];
   __shared__ double s_core[kHT / 32][kHB];
@@ -321,83 +387,159 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
   const long long t_begin = clock64();
   long long t_eval = 0;
 
-  const int span = 2 * max(qb, nb - 1 - qb) + 1;
-  for (int base = 0; base < span; base += 32) {
-    // pruning bound: my best so far and whatever my component has already published.  U[ca] is ONE address per
-    // component: in the late rounds (2..40 components) every warp of the grid polling it at every step serialises on a
-    // few L2 lines (measured: 71 ms per round at 480 k points whatever the real work) -- poll every 8th step; a stale
-    // value is only a weaker (still valid) upper bound.
-    if (((base >> 5) & 7) == 0) ucache = valid ? u2d(*(volatile uint64_t*)&U[ca]) : INFINITY;
-    double bnd = valid ? fmin(bw, ucache) : -1.0;
-    if (core_a > bnd) bnd = -1.0;  // nothing at this lane can still win (w >= core_a)
-    const double wb = warp_max_d(bnd);
+  const int qg = qb >> 5, ng = (nb + 31) >> 5;
+  const int gspan = 2 * max(qg, ng - 1 - qg) + 1;
+  // pruning bound of a lane: its best so far and whatever its component has already published (a stale value of U is
+  // only a weaker, still valid, upper bound); -1 once nothing at this lane can win any more (w >= core_a)
+  auto lane_bound = [&]() {
+    ucache = valid ? u2d(*(volatile uint64_t*)&U[ca]) : INFINITY;
+    double b = valid ? fmin(bw, ucache) : -1.0;
+    if (core_a > b) b = -1.0;
+    return b;
+  };
+  for (int gbase = 0; gbase < gspan; gbase += 32) {
+    double bnd = lane_bound();
+    double wb = warp_max_d(bnd);
     if (wb < 0.0) break;           // every lane of the block is settled
     ++st_steps;
-    const double wba = wb * alpha;                              // bound on the raw distance (w >= d / alpha)
-    const double wb2 = wba * wba * (1.0 + 8.0 * DBL_EPSILON);  // squared-space bound, rounded up
-    const int cb = sweep_block(qb, base + lane);
-    bool pass = cb >= 0 && cb < nb;
-    if (pass) {
-      const int bc = bcomp[cb];
-      pass = !(qc >= 0 && bc == qc) && fmax(bmincore[cb], qmin) <= wb &&
-             box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb2;
-    }
-    unsigned mask = __ballot_sync(0xffffffffu, pass);
+    double wba = wb * alpha;                              // bound on the raw distance (w >= d / alpha)
+    double wb2 = wba * wba * (1.0 + 8.0 * DBL_EPSILON);  // squared-space bound, rounded up
+    const int cg = sweep_block(qg, gbase + lane);
+    bool gpass = cg >= 0 && cg < ng;
+    if (gpass)
+      gpass = !(qc >= 0 && gcomp[cg] == qc) && fmax(gmincore[cg], qmin) <= wb &&
+              box_box_lb2<D>(qlo, qhi, glo + (int64_t)cg * D, ghi + (int64_t)cg * D) <= wb2;
+    unsigned gmask = __ballot_sync(0xffffffffu, gpass);
     const long long t_e0 = clock64();
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int blk = __shfl_sync(0xffffffffu, cb, src);
-      const int64_t p0 = (int64_t)blk * kHB;
-      const int cnt = (int)min((int64_t)kHB, n - p0);
-      // The box-to-box test above uses the LOOSEST bound of the 32 lanes: one lane with a far best candidate (a block
-      // straddling two clusters, an outlier) would drag the whole warp through every block point by point (measured:
-      // a single warp spending 135 M cycles = the entire 71 ms of a late round).  Per lane: point-to-box bound against
-      // the lane's OWN pruning bound; the block is staged only if some lane still wants it.
-      bool want = false;
-      if (bnd >= 0.0 && fmax(core_a, bmincore[blk]) <= bnd) {
-        const double ba = bnd * alpha;
-        want = point_box_lb2<D>(q, blo + (int64_t)blk * D, bhi + (int64_t)blk * D) <= ba * ba * (1.0 + 8.0 * DBL_EPSILON);
+    while (gmask) {
+      const int gsrc = __ffs(gmask) - 1;
+      gmask &= gmask - 1;
+      const int grp = __shfl_sync(0xffffffffu, cg, gsrc);
+      // the bound may have tightened since the group test
+      bnd = lane_bound();
+      wb = warp_max_d(bnd);
+      if (wb < 0.0) break;
+      ++st_steps;
+      wba = wb * alpha;
+      wb2 = wba * wba * (1.0 + 8.0 * DBL_EPSILON);
+      const int cb = grp * 32 + lane;
+      bool pass = cb < nb;
+      if (pass) {
+        const int bc = bcomp[cb];
+        pass = !(qc >= 0 && bc == qc) && fmax(bmincore[cb], qmin) <= wb &&
+               box_box_lb2<D>(qlo, qhi, blo + (int64_t)cb * D, bhi + (int64_t)cb * D) <= wb2;
       }
-      if (!__any_sync(0xffffffffu, want)) continue;
-      ++st_blocks;
-      __syncwarp();
-      for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
-      if (lane < cnt) {
-        s_core[wib][lane] = core_sorted[p0 + lane];
-        s_comp[wib][lane] = comp[p0 + lane];
-        s_oid[wib][lane] = sids[p0 + lane];
-      }
-      __syncwarp();
-      if (want) {
-        for (int j = 0; j < cnt; ++j) {
-          if (s_comp[wib][j] == ca) continue;
-          double w = fmax(core_a, s_core[wib][j]);
-          if (w > bnd) continue;
-          ++st_pairs;
-          const double d2 = sqdist_rn<D>(q, &s_pts[wib][j * D]);
+      unsigned mask = __ballot_sync(0xffffffffu, pass);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int blk = __shfl_sync(0xffffffffu, cb, src);
+        const int64_t p0 = (int64_t)blk * kHB;
+        const int cnt = (int)min((int64_t)kHB, n - p0);
+        // The box-to-box tests use the LOOSEST bound of the 32 lanes: one lane with a far best candidate (a block
+        // straddling two clusters, an outlier) would drag the whole warp through every block point by point (measured:
+        // a single warp spending 135 M cycles = the entire 71 ms of a late round).  Per lane: point-to-box bound against
+        // the lane's OWN pruning bound; the block is staged only if some lane still wants it.
+        bool want = false;
+        if (bnd >= 0.0 && fmax(core_a, bmincore[blk]) <= bnd) {
           const double ba = bnd * alpha;
-          if (d2 > ba * ba * (1.0 + 8.0 * DBL_EPSILON)) continue;
-          const double dist = __ddiv_rn(__dsqrt_rn(d2), alpha);
-          w = fmax(w, dist);
-          const int oj = s_oid[wib][j];
-          const int lo = min(oa, oj), hi = max(oa, oj);
-          const bool better = (w < bw) || (w == bw && (lo < blo_id || (lo == blo_id && hi < bhi_id)));
-          if (better) {
-            bw = w;
-            bj = (int)(p0 + j);
-            blo_id = lo;
-            bhi_id = hi;
-            if (w < bnd) bnd = w;
+          want = point_box_lb2<D>(q, blo + (int64_t)blk * D, bhi + (int64_t)blk * D) <= ba * ba * (1.0 + 8.0 * DBL_EPSILON);
+        }
+        if (!__any_sync(0xffffffffu, want)) continue;
+        ++st_blocks;
+        __syncwarp();
+        for (int e = lane; e < cnt * D; e += 32) s_pts[wib][e] = __ldg(&P[p0 * D + e]);
+        if (lane < cnt) {
+          s_core[wib][lane] = core_sorted[p0 + lane];
+          s_comp[wib][lane] = comp[p0 + lane];
+          s_oid[wib][lane] = sids[p0 + lane];
+        }
+        __syncwarp();
+        const unsigned wmask = __ballot_sync(0xffffffffu, want);
+        if (__popc(wmask) <= kHdbParLanes) {
+          // Few lanes still want this block (the usual case in the late rounds: a far, isolated component has a large
+          // bound and its warps visit ~1000 blocks each with 1-3 interested lanes).  Turn the loop around: for each
+          // interested query lane, the 32 lanes evaluate the block's 32 candidates in parallel and a warp argmin under the
+          // strict (w, min id, max id) order hands the winner back -- ~32x fewer serial fp64 chains than lane-per-query.
+          unsigned rem = wmask;
+          while (rem) {
+            const int L = __ffs(rem) - 1;
+            rem &= rem - 1;
+            double ql[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) ql[d] = __shfl_sync(0xffffffffu, q[d], L);
+            const double coreL = __shfl_sync(0xffffffffu, core_a, L), bndL = __shfl_sync(0xffffffffu, bnd, L);
+            const int caL = __shfl_sync(0xffffffffu, ca, L), oaL = __shfl_sync(0xffffffffu, oa, L);
+            double w = INFINITY;
+            int lo = 0x7fffffff, hi = 0x7fffffff, idx = lane;
+            if (lane < cnt && s_comp[wib][lane] != caL) {
+              double ww = fmax(coreL, s_core[wib][lane]);
+              if (ww <= bndL) {
+                ++st_pairs;
+                const double d2 = sqdist_rn<D>(ql, &s_pts[wib][lane * D]);
+                const double ba = bndL * alpha;
+                if (d2 <= ba * ba * (1.0 + 8.0 * DBL_EPSILON)) {
+                  ww = fmax(ww, __ddiv_rn(__dsqrt_rn(d2), alpha));
+                  const int oj = s_oid[wib][lane];
+                  w = ww;
+                  lo = min(oaL, oj);
+                  hi = max(oaL, oj);
+                }
+              }
+            }
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+              const double w2 = __shfl_xor_sync(0xffffffffu, w, sft);
+              const int lo2 = __shfl_xor_sync(0xffffffffu, lo, sft), hi2 = __shfl_xor_sync(0xffffffffu, hi, sft);
+              const int idx2 = __shfl_xor_sync(0xffffffffu, idx, sft);
+              if (w2 < w || (w2 == w && (lo2 < lo || (lo2 == lo && hi2 < hi)))) {
+                w = w2;
+                lo = lo2;
+                hi = hi2;
+                idx = idx2;
+              }
+            }
+            if (lane == L && w < INFINITY) {
+              const bool better = (w < bw) || (w == bw && (lo < blo_id || (lo == blo_id && hi < bhi_id)));
+              if (better) {
+                bw = w;
+                bj = (int)(p0 + idx);
+                blo_id = lo;
+                bhi_id = hi;
+                if (w < bnd) bnd = w;
+              }
+            }
+          }
+        } else if (want) {
+          for (int j = 0; j < cnt; ++j) {
+            if (s_comp[wib][j] == ca) continue;
+            double w = fmax(core_a, s_core[wib][j]);
+            if (w > bnd) continue;
+            ++st_pairs;
+            const double d2 = sqdist_rn<D>(q, &s_pts[wib][j * D]);
+            const double ba = bnd * alpha;
+            if (d2 > ba * ba * (1.0 + 8.0 * DBL_EPSILON)) continue;
+            const double dist = __ddiv_rn(__dsqrt_rn(d2), alpha);
+            w = fmax(w, dist);
+            const int oj = s_oid[wib][j];
+            const int lo = min(oa, oj), hi = max(oa, oj);
+            const bool better = (w < bw) || (w == bw && (lo < blo_id || (lo == blo_id && hi < bhi_id)));
+            if (better) {
+              bw = w;
+              bj = (int)(p0 + j);
+              blo_id = lo;
+              bhi_id = hi;
+              if (w < bnd) bnd = w;
+            }
           }
         }
       }
+      if (valid && bw < published) {
+        atomicMin((unsigned long long*)&U[ca], (unsigned long long)__double_as_longlong(bw));
+        published = bw;
+      }
     }
     t_eval += clock64() - t_e0;
-    if (valid && bw < published) {
-      atomicMin((unsigned long long*)&U[ca], (unsigned long long)__double_as_longlong(bw));
-      published = bw;
-    }
   }
   if (valid) {
     bestw[a] = bw;
@@ -412,7 +554,7 @@ __global__ void __launch_bounds__(kHT) hdb_search_kernel(
       atomicAdd(&g_hdb_stats[round * 4 + 0], (unsigned long long)st_steps);
       atomicAdd(&g_hdb_stats[round * 4 + 1], (unsigned long long)st_blocks);
       atomicAdd(&g_hdb_stats[round * 4 + 2], (unsigned long long)pr);
-      atomicAdd(&g_hdb_stats[round * 4 + 3], (unsigned long long)(st_steps * 32 >= (unsigned)(2 * max(qb, nb - 1 - qb) + 1)));
+      atomicAdd(&g_hdb_stats[round * 4 + 3], 1ull);   // warps that ran
       const unsigned long long tt = (unsigned long long)(clock64() - t_begin);
       atomicAdd(&g_hdb_clk[round * 4 + 0], tt);
       atomicMax(&g_hdb_clk[round * 4 + 1], tt);
@@ -494,9 +636,9 @@ struct HdbLayout {
   uint32_t* status;
   int32_t* n_edges;
   uint64_t *keys, *skeys, *U, *E, *edge_uv, *edge_uv2;
-  int32_t *ids, *sids, *inv, *comp, *next, *bcomp, *bestp;
-  float *P, *blo, *bhi;
-  double *core_sorted, *bmincore, *bestw, *edge_w, *edge_w2;
+  int32_t *ids, *sids, *inv, *comp, *next, *bcomp, *bestp, *gcomp;
+  float *P, *blo, *bhi, *glo, *ghi;
+  double *core_sorted, *bmincore, *bestw, *edge_w, *edge_w2, *gmincore;
   void* cub_ws;
   size_t cub_bytes, total;
 };
@@ -531,6 +673,13 @@ static HdbLayout hdb_layout(int64_t n, int D, void* base) {
   L.bhi = (float*)take(4 * nb * D);
   L.core_sorted = (double*)take(8 * n);
   L.bmincore = (double*)take(8 * nb);
+  {
+    const int64_t ng = (nb + 31) / 32;
+    L.glo = (float*)take(4 * ng * D);
+    L.ghi = (float*)take(4 * ng * D);
+    L.gmincore = (double*)take(8 * ng);
+    L.gcomp = (int32_t*)take(4 * ng);
+  }
   L.bestw = (double*)take(8 * n);
   L.edge_w = (double*)take(8 * n);
   L.edge_w2 = (double*)take(8 * n);
@@ -565,14 +714,18 @@ static int hdb_mst_impl(const float* X, int64_t n, int k, double alpha, double* 
   PGS_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_ws, cb, L.keys, L.skeys, L.ids, L.sids, (int)n, 0, 64, s));
   hdb_gather_kernel<<<gp, kHT, 0, s>>>(X, L.sids, n, D, L.P, L.inv);
   hdb_block_box_kernel<D><<<gw, kHT, 0, s>>>(L.P, n, nb, L.blo, L.bhi);
-  count_launch(2);
-  if (k <= 8)
-    hdb_knn_kernel<D, 8><<<gw, kHT, 0, s>>>(L.P, L.sids, n, nb, L.blo, L.bhi, k, L.core_sorted, core);
-  else
-    hdb_knn_kernel<D, 32><<<gw, kHT, 0, s>>>(L.P, L.sids, n, nb, L.blo, L.bhi, k, L.core_sorted, core);
-  hdb_block_core_kernel<<<gw, kHT, 0, s>>>(L.core_sorted, n, nb, L.bmincore);
-  hdb_iota_kernel<<<gp, kHT, 0, s>>>(L.comp, n);
+  const int ng = (nb + 31) / 32;
+  const unsigned gg = blocks_for((int64_t)ng * 32);
+  hdb_group_box_kernel<D><<<gg, kHT, 0, s>>>(L.blo, L.bhi, nb, ng, L.glo, L.ghi);
   count_launch(3);
+  if (k <= 8)
+    hdb_knn_kernel<D, 8><<<gw, kHT, 0, s>>>(L.P, L.sids, n, nb, L.blo, L.bhi, L.glo, L.ghi, k, L.core_sorted, core);
+  else
+    hdb_knn_kernel<D, 32><<<gw, kHT, 0, s>>>(L.P, L.sids, n, nb, L.blo, L.bhi, L.glo, L.ghi, k, L.core_sorted, core);
+  hdb_block_core_kernel<<<gw, kHT, 0, s>>>(L.core_sorted, n, nb, L.bmincore);
+  hdb_group_meta_kernel<<<gg, kHT, 0, s>>>(L.bmincore, nullptr, nb, ng, L.gmincore, nullptr);
+  hdb_iota_kernel<<<gp, kHT, 0, s>>>(L.comp, n);
+  count_launch(4);
   PGS_CHECK_LAUNCH();
   uint32_t status_h = 0;
   PGS_CUDA(cudaMemcpyAsync(&status_h, L.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -595,8 +748,11 @@ static int hdb_mst_impl(const float* X, int64_t n, int k, double alpha, double* 
       return PGS_ERR_CUDA;
     }
     hdb_round_init_kernel<<<blocks_for((int64_t)nb * 32), kHT, 0, s>>>(L.comp, n, nb, L.bcomp, L.U, L.E);
+    hdb_group_meta_kernel<<<gg, kHT, 0, s>>>(nullptr, L.bcomp, nb, ng, nullptr, L.gcomp);
     hdb_search_kernel<D><<<gw, kHT, 0, s>>>(L.P, L.sids, L.core_sorted, L.comp, n, nb, L.blo, L.bhi, L.bmincore,
-                                            L.bcomp, alpha, L.U, L.bestw, L.bestp, rounds);
+                                            L.bcomp, L.glo, L.ghi, L.gmincore, L.gcomp, alpha, L.U, L.bestw, L.bestp,
+                                            rounds);
+    count_launch();
     hdb_select_kernel<<<gp, kHT, 0, s>>>(L.sids, L.comp, L.bestw, L.bestp, n, L.U, L.E);
     hdb_merge_kernel<<<gp, kHT, 0, s>>>(L.comp, L.inv, n, L.U, L.E, L.next, L.edge_uv, L.edge_w, L.n_edges);
     hdb_relabel_kernel<<<gp, kHT, 0, s>>>(L.comp, L.next, n);
