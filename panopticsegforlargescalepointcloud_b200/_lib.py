@@ -160,3 +160,21 @@ def ptr(t):
 
 def launch_count():
     return int(load().pgs_launch_count())
+
+
+class nvtx_range:
+    """NVTX range around a host-side phase (coordinate / kernel maps, region growing, HDBSCAN, ...): visible in Nsight
+    Systems and `ncu --nvtx`; a no-op costing two cheap calls when no tool is attached."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if torch.cuda.is_available():
+            torch.cuda.nvtx.range_pop()
+        return False

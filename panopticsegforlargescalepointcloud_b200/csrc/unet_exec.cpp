@@ -5,6 +5,8 @@
 // Reference control flow being replaced: torch_points3d/applications/minkowski.py:160-196 (skip stack),
 // modules/MinkowskiEngine/api_modules.py:76-82 (residual block), 281-285 (ResNetDown), 306-311 (ResNetUp), and
 // autograd's reverse walk over the same graph.
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 #include <vector>
 
 #include "common.cuh"
@@ -48,6 +50,10 @@ int pgs_unet_forward(const pgs_unet_op* ops, int32_t n_ops, int32_t n_slots, flo
                      const int64_t* slot_n, const int32_t* slot_c, const pgs_unet_conv* convs, const pgs_unet_bn* bns,
                      double* sums, float* stats, const int64_t* stat_off, void* stream) {
   PGS_CHECK_ARG(ops && slot_ptr && slot_n && slot_c && n_ops >= 0 && n_slots >= 1, "bad tape");
+  struct Range {
+    Range(const char* n) { nvtxRangePushA(n); }
+    ~Range() { nvtxRangePop(); }
+  } range("pgs_unet_forward");
   for (int32_t i = 0; i < n_ops; ++i) {
     const pgs_unet_op& op = ops[i];
     PGS_CHECK_ARG(op.a >= 0 && op.a < n_slots && op.dst > 0 && op.dst < n_slots && op.b < n_slots, "slot out of range");
@@ -109,6 +115,10 @@ int pgs_unet_backward(const pgs_unet_op* ops, int32_t n_ops, int32_t n_slots, in
                       int64_t garena_elems, float** grad_in, int32_t* n_grad_in, void* stream, void* side_stream) {
   PGS_CHECK_ARG(ops && slot_ptr && slot_n && slot_c && grad_in && n_grad_in, "bad tape");
   PGS_CHECK_ARG(out_slot >= 0 && out_slot < n_slots, "output slot out of range");
+  struct Range {
+    Range(const char* n) { nvtxRangePushA(n); }
+    ~Range() { nvtxRangePop(); }
+  } range("pgs_unet_backward");
   cudaStream_t s_main = (cudaStream_t)stream, s_side = (cudaStream_t)side_stream;
   std::vector<std::vector<const float*>> glist((size_t)n_slots);
   glist[out_slot].push_back(d_out);

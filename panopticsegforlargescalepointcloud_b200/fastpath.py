@@ -204,62 +204,66 @@ class _UNetFn(torch.autograd.Function):
         # stream in order of first use, so that the tables of the deeper levels are built while the first layers
         # already run (each convolution waits for the event of its own tables).
         need_bwd = any(ctx.needs_input_grad)
-        maps_side = MAPS_SIDE_STREAM
-        if maps_side:
-            t = {0: ts0}
-            for kind, a, b, dst, idx, relu in prog.ops:
-                t[dst] = t[a]
-                if kind == OP_CONV:
-                    mod = prog.convs[idx]
-                    if mod.stride > 1:
-                        if mod.TRANSPOSE:
-                            t[dst] = t[a] // mod.stride
-                        else:
-                            t[dst] = t[a] * mod.stride
-                            cm.stride(t[a], t[dst])
-            main = torch.cuda.current_stream(dev)
-            side = _side_stream(dev)
-            side.wait_stream(main)   # the coordinate maps; and everything the previous step still reads from old tables
-        cinfo = [None] * len(prog.convs)
-        cevent = [None] * len(prog.convs)
-        with (torch.cuda.stream(side) if maps_side else contextlib.nullcontext()):
-            for kind, a, b, dst, idx, relu in prog.ops:
-                if kind == OP_CONV:
-                    mod = prog.convs[idx]
-                    if C[a] != mod.in_channels:
-                        raise ValueError("expected %d input channels, got %d" % (mod.in_channels, C[a]))
-                    K = mod.kernel_size ** 3
-                    before = len(cm.kmaps)
-                    km_f, km_b, mf, mb, ts_out, n_out = mod.maps_for(cm, ts[a], n[a])
-                    kind_f = ME._conv_kernel_choice(lib, K, mod.in_channels, mod.out_channels, n_out, km_f is not None)
-                    kind_b = ME._conv_kernel_choice(lib, K, mod.out_channels, mod.in_channels, n[a], km_b is not None)
-                    if maps_side and km_f is not None:
-                        fresh = len(cm.kmaps) != before
-                        for km, kd, nq in ((km_f, kind_f, n_out), (km_b, kind_b, n[a])):
-                            if (kd != "ffma" and ME.SORT_TABLES and nq >= ME.SORT_MIN_ROWS and km._sorted is None
-                                    and (km is km_f or need_bwd)):
-                                km.sorted()
+        torch.cuda.nvtx.range_push("pgs.unet.maps")       # pass 1: coordinate / kernel maps (closed before pass 2)
+        try:
+            maps_side = MAPS_SIDE_STREAM
+            if maps_side:
+                t = {0: ts0}
+                for kind, a, b, dst, idx, relu in prog.ops:
+                    t[dst] = t[a]
+                    if kind == OP_CONV:
+                        mod = prog.convs[idx]
+                        if mod.stride > 1:
+                            if mod.TRANSPOSE:
+                                t[dst] = t[a] // mod.stride
+                            else:
+                                t[dst] = t[a] * mod.stride
+                                cm.stride(t[a], t[dst])
+                main = torch.cuda.current_stream(dev)
+                side = _side_stream(dev)
+                side.wait_stream(main)   # the coordinate maps; and everything the previous step still reads from old tables
+            cinfo = [None] * len(prog.convs)
+            cevent = [None] * len(prog.convs)
+            with (torch.cuda.stream(side) if maps_side else contextlib.nullcontext()):
+                for kind, a, b, dst, idx, relu in prog.ops:
+                    if kind == OP_CONV:
+                        mod = prog.convs[idx]
+                        if C[a] != mod.in_channels:
+                            raise ValueError("expected %d input channels, got %d" % (mod.in_channels, C[a]))
+                        K = mod.kernel_size ** 3
+                        before = len(cm.kmaps)
+                        km_f, km_b, mf, mb, ts_out, n_out = mod.maps_for(cm, ts[a], n[a])
+                        kind_f = ME._conv_kernel_choice(lib, K, mod.in_channels, mod.out_channels, n_out, km_f is not None)
+                        kind_b = ME._conv_kernel_choice(lib, K, mod.out_channels, mod.in_channels, n[a], km_b is not None)
+                        if maps_side and km_f is not None:
+                            fresh = len(cm.kmaps) != before
+                            for km, kd, nq in ((km_f, kind_f, n_out), (km_b, kind_b, n[a])):
+                                if (kd != "ffma" and ME.SORT_TABLES and nq >= ME.SORT_MIN_ROWS and km._sorted is None
+                                        and (km is km_f or need_bwd)):
+                                    km.sorted()
+                                    fresh = True
+                            if need_bwd and km_f._pairs is None:
+                                km_f.pairs()
                                 fresh = True
-                        if need_bwd and km_f._pairs is None:
-                            km_f.pairs()
-                            fresh = True
-                        if fresh:
-                            cevent[idx] = torch.cuda.Event()
-                            cevent[idx].record(side)
-                    cinfo[idx] = (km_f, km_b, mf, mb, K, kind_f, kind_b)
-                    n[dst], C[dst], ts[dst] = n_out, mod.out_channels, ts_out
-                elif kind == OP_BN:
-                    if prog.bns[idx].bn.momentum is None:
-                        raise Unsupported("cumulative-average batch norm")
-                    n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
-                elif kind == OP_ADD:
-                    if (n[a], C[a], ts[a]) != (n[b], C[b], ts[b]):
-                        raise ValueError("sum of sparse tensors on different maps")
-                    n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
-                else:
-                    if (n[a], ts[a]) != (n[b], ts[b]):
-                        raise ValueError("concatenation of sparse tensors on different maps")
-                    n[dst], C[dst], ts[dst] = n[a], C[a] + C[b], ts[a]
+                            if fresh:
+                                cevent[idx] = torch.cuda.Event()
+                                cevent[idx].record(side)
+                        cinfo[idx] = (km_f, km_b, mf, mb, K, kind_f, kind_b)
+                        n[dst], C[dst], ts[dst] = n_out, mod.out_channels, ts_out
+                    elif kind == OP_BN:
+                        if prog.bns[idx].bn.momentum is None:
+                            raise Unsupported("cumulative-average batch norm")
+                        n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
+                    elif kind == OP_ADD:
+                        if (n[a], C[a], ts[a]) != (n[b], C[b], ts[b]):
+                            raise ValueError("sum of sparse tensors on different maps")
+                        n[dst], C[dst], ts[dst] = n[a], C[a], ts[a]
+                    else:
+                        if (n[a], ts[a]) != (n[b], ts[b]):
+                            raise ValueError("concatenation of sparse tensors on different maps")
+                        n[dst], C[dst], ts[dst] = n[a], C[a] + C[b], ts[a]
+        finally:
+            torch.cuda.nvtx.range_pop()
         if min(n) <= 0:
             raise Unsupported("empty level")
         # ---- arenas ----

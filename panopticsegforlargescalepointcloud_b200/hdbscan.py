@@ -69,8 +69,9 @@ class HDBSCAN:
         nb = lib.pgs_hdb_scratch_bytes(n, D)
         scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
         rounds = np.zeros(1, np.int32)
-        check(lib.pgs_hdb_mst(ptr(X), n, D, k, self.alpha, ptr(core), ptr(u), ptr(v), ptr(w),
-                              rounds.ctypes.data, ptr(scratch), nb, stream_ptr()))
+        with _lib.nvtx_range("pgs.hdbscan.mst"):
+            check(lib.pgs_hdb_mst(ptr(X), n, D, k, self.alpha, ptr(core), ptr(u), ptr(v), ptr(w),
+                                  rounds.ctypes.data, ptr(scratch), nb, stream_ptr()))
         self.boruvka_rounds_ = int(rounds[0])
         # host tree stage over pinned buffers
         u_h = torch.empty(n - 1, dtype=torch.int32, pin_memory=True)
@@ -82,8 +83,9 @@ class HDBSCAN:
         torch.cuda.current_stream().synchronize()
         labels_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
         ncl = np.zeros(1, np.int32)
-        check(lib.pgs_hdb_labels_host(u_h.data_ptr(), v_h.data_ptr(), w_h.data_ptr(), n, self.min_cluster_size,
-                                      self.cluster_selection_epsilon, labels_h.data_ptr(), ncl.ctypes.data))
+        with _lib.nvtx_range("pgs.hdbscan.tree_host"):
+            check(lib.pgs_hdb_labels_host(u_h.data_ptr(), v_h.data_ptr(), w_h.data_ptr(), n, self.min_cluster_size,
+                                          self.cluster_selection_epsilon, labels_h.data_ptr(), ncl.ctypes.data))
         self.core_distances_ = core
         self.mst_ = (u, v, w)
         self.n_clusters_ = int(ncl[0])

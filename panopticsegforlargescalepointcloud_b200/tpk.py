@@ -155,7 +155,8 @@ def region_grow(pos, labels, batch, ignore_labels=[], nsample=300, radius=0.03, 
     if nb * nl >= _MAX_GID:
         raise ValueError("too many (class, scene) groups for one region_grow call: %d" % (nb * nl))
     gid = torch.where(valid, (labels - lmin) * nb + batch, torch.full_like(labels, -1)).to(torch.int32).contiguous()
-    root, _, _ = grow_labels(p, gid, radius, nsample)
+    with _lib.nvtx_range("pgs.region_grow.grow_labels"):
+        root, _, _ = grow_labels(p, gid, radius, nsample)
     rootl = root.long()
     size = torch.bincount(rootl[valid], minlength=n)
     keep = valid & (size[rootl.clamp_min(0)] >= int(min_cluster_size))
