@@ -217,10 +217,12 @@ int pgs_bq_export(const int32_t* nbr, const float* dist, const int32_t* cnt, int
 
 /* Region growing == min-ancestor labelling over the directed edges q -> nbr[q][*]:
  * label[v] = smallest row index that reaches v.  pgs_rg_propagate runs `rounds` (push + pointer-jump)
- * sweeps and leaves *changed != 0 if any label moved; call until it reads 0. */
+ * sweeps and leaves *changed != 0 if any label moved; call until it reads 0.
+ * pushed (nullable): int32 [n] frontier state, filled with -1 by the caller before the first call -- a row only pushes
+ * again when its label moved since its last push (exact: atomicMin is monotone); NULL = every row pushes in every sweep. */
 int pgs_rg_init(const int32_t* gid, int64_t n, int32_t* label, void* stream);
 int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid, int64_t n, int32_t nsample,
-                     int32_t rounds, int32_t* label, int32_t* changed, void* stream);
+                     int32_t rounds, int32_t* label, int32_t* pushed, int32_t* changed, void* stream);
 
 /* Nearest support point of every query (k = 1) on the grid built by pgs_bq_grid_build (cell >= the typical point spacing);
  * replaces torch_geometric.nn.knn(x, y, k=1) of the eval-time back-projection (reference:

@@ -46,7 +46,7 @@ SIGNATURES = {
     "pgs_prop_cross_nms": (c_int, [c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "pgs_rg_init": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    "pgs_rg_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+    "pgs_rg_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
     "pgs_hdb_scratch_bytes": (c_size_t, [c_int64, c_int32]),
     "pgs_hdb_search_stats": (c_int, [c_void_p, c_int32]),

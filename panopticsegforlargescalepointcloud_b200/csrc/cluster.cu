@@ -293,13 +293,29 @@ __global__ void __launch_bounds__(kCT) rg_init_kernel(const int32_t* __restrict_
 template <int LANES>
 __global__ void __launch_bounds__(kCT) rg_push_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ cnt,
                                                        const int32_t* __restrict__ gid, int64_t n, int nsample,
-                                                       int32_t* __restrict__ label, int32_t* __restrict__ changed) {
+                                                       int32_t* __restrict__ label, int32_t* __restrict__ pushed,
+                                                       int32_t* __restrict__ changed) {
   const int lane = threadIdx.x & (LANES - 1);
   const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
   if (q >= n || gid[q] < 0) return;
+  // the LANES lanes of a row agree on ONE snapshot of the row's label (lane 0 reads, the group shuffles): they all push the
+  // same value and take the same frontier decision
+  const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31) / LANES * LANES));
+  int mine = 0, prev = -1;
+  if (lane == 0) {
+    mine = *(volatile int32_t*)&label[q];
+    if (pushed) prev = pushed[q];
+  }
+  mine = __shfl_sync(gmask, mine, 0, LANES);
+  prev = __shfl_sync(gmask, prev, 0, LANES);
+  // frontier: a row whose label has not moved since it last pushed has nothing new to tell its neighbours (atomicMin is
+  // monotone, so label[j] <= pushed[q] already holds for every out-edge); later sweeps only touch the rows that changed
+  if (pushed) {
+    if (prev == mine) return;
+    if (lane == 0) pushed[q] = mine;
+  }
   const int c = cnt[q];
   const int32_t* row = nbr + q * nsample;
-  const int mine = *(volatile int32_t*)&label[q];
   bool any = false;
   for (int e = lane; e < c; e += LANES) {
     const int j = row[e];
@@ -535,7 +551,7 @@ int pgs_rg_init(const int32_t* gid, int64_t n, int32_t* label, void* stream) {
 }
 
 int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid, int64_t n, int32_t nsample,
-                     int32_t rounds, int32_t* label, int32_t* changed, void* stream) {
+                     int32_t rounds, int32_t* label, int32_t* pushed, int32_t* changed, void* stream) {
   if (n == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   PGS_CUDA(cudaMemsetAsync(changed, 0, sizeof(int32_t), s));
@@ -547,9 +563,9 @@ int pgs_rg_propagate(const int32_t* nbr, const int32_t* cnt, const int32_t* gid,
   const int64_t threads = n * lanes;
   for (int r = 0; r < rounds; ++r) {
     if (lanes == 32)
-      rg_push_kernel<32><<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, changed);
+      rg_push_kernel<32><<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, pushed, changed);
     else
-      rg_push_kernel<8><<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, changed);
+      rg_push_kernel<8><<<(unsigned)((threads + kCT - 1) / kCT), kCT, 0, s>>>(nbr, cnt, gid, n, nsample, label, pushed, changed);
     rg_jump_kernel<<<grid_for_c(n), kCT, 0, s>>>(n, label, changed);
     count_launch(2);
   }

@@ -120,9 +120,10 @@ def grow_labels(pos, gid, radius, nsample):
     nbr, cnt, _ = _query(grid, grid.spos, grid.skeys, n, n, radius, nsample, False)
     label = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     changed = torch.zeros(1, dtype=torch.int32, device=dev)
+    pushed = torch.full((max(n, 1),), -1, dtype=torch.int32, device=dev)     # frontier: label at a row's last push
     check(lib.pgs_rg_init(ptr(gid), n, ptr(label), stream_ptr()))
     for _ in range(4096):
-        check(lib.pgs_rg_propagate(ptr(nbr), ptr(cnt), ptr(gid), n, nsample, 2, ptr(label), ptr(changed),
+        check(lib.pgs_rg_propagate(ptr(nbr), ptr(cnt), ptr(gid), n, nsample, 2, ptr(label), ptr(pushed), ptr(changed),
                                    stream_ptr()))
         if int(changed) == 0:
             break
