@@ -147,5 +147,9 @@ def test_backward_after_another_forward_rearranges_its_weights(cuda_device):
     clean, out0 = grads(False)
     mixed, out1 = grads(True)
     assert float((out0 - out1).abs().max()) <= 2e-5 * max(1.0, float(out0.abs().max()))   # (few-row layers sum by atomicAdd)
+    # run-to-run differences come from the order of fp32 atomic adds alone, amplified by the 3..50-row coarse levels of this
+    # small scene (two clean runs differ by up to 4e-3 on single tensors); stale or foreign weight layouts give O(1)
     worst = max(float((x - y).norm() / y.norm().clamp_min(1e-12)) for x, y in zip(mixed, clean))
-    assert worst <= 1e-3, worst       # (atomic-add ordering only; stale or foreign weight layouts give O(1))
+    ga = torch.cat([x.reshape(-1) for x in mixed]).double()
+    gb = torch.cat([x.reshape(-1) for x in clean]).double()
+    assert worst <= 2e-2 and 1.0 - float(torch.dot(ga, gb) / (ga.norm() * gb.norm())) <= 1e-6, worst
