@@ -278,6 +278,11 @@ int pgs_hdb_search_stats(int64_t* out_host, int32_t max_rounds);
 int pgs_hdb_mst(const float* X, int64_t n, int32_t D, int32_t min_samples, double alpha,
                 double* core, int32_t* u, int32_t* v, double* w, int32_t* rounds_host,
                 void* scratch, size_t scratch_bytes, void* stream);
+/* rank_out int32 [n] (device): position of every input row in the Morton order pgs_hdb_mst sorted the points by, read
+ * from the `scratch` of that call (same n, D).  Relabelling the MST's endpoints with it (keeping each edge's (u, v) order)
+ * gives the host tree stage an isomorphic tree whose leaves sit next to their spatial neighbours -- the union-find and
+ * the condensed-tree walk then stay in cache; the labels come back per rank and are permuted back by the caller. */
+int pgs_hdb_morton_rank(const void* scratch, int64_t n, int32_t D, int32_t* rank_out, void* stream);
 int pgs_hdb_labels_host(const int32_t* u_host, const int32_t* v_host, const double* w_host, int64_t n,
                         int32_t min_cluster_size, double cluster_selection_epsilon,
                         int32_t* labels_host, int32_t* n_clusters_host);

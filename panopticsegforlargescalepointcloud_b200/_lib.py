@@ -50,6 +50,7 @@ SIGNATURES = {
                                  c_void_p]),
     "pgs_hdb_scratch_bytes": (c_size_t, [c_int64, c_int32]),
     "pgs_hdb_search_stats": (c_int, [c_void_p, c_int32]),
+    "pgs_hdb_morton_rank": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "pgs_hdb_mst": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_size_t, c_void_p]),
     "pgs_hdb_labels_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_void_p, c_void_p]),

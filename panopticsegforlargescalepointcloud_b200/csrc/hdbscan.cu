@@ -786,6 +786,13 @@ using namespace pgs;
 
 extern "C" {
 
+int pgs_hdb_morton_rank(const void* scratch, int64_t n, int32_t D, int32_t* rank_out, void* stream) {
+  PGS_CHECK_ARG(scratch != nullptr && rank_out != nullptr && n >= 1 && D >= 1 && D <= 8, "bad arguments");
+  HdbLayout L = hdb_layout(n, D, const_cast<void*>(scratch));
+  PGS_CUDA(cudaMemcpyAsync(rank_out, L.inv, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return PGS_OK;
+}
+
 int pgs_hdb_search_stats(int64_t* out_host, int32_t max_rounds) {
   unsigned long long h[64 * 4];
   PGS_CUDA(cudaMemcpyFromSymbol(h, g_hdb_stats, sizeof(h)));

@@ -73,23 +73,29 @@ class HDBSCAN:
             check(lib.pgs_hdb_mst(ptr(X), n, D, k, self.alpha, ptr(core), ptr(u), ptr(v), ptr(w),
                                   rounds.ctypes.data, ptr(scratch), nb, stream_ptr()))
         self.boruvka_rounds_ = int(rounds[0])
-        # host tree stage over pinned buffers
+        # host tree stage over pinned buffers.  The endpoints go to the host as MORTON RANKS (each edge keeps its (u, v)
+        # order, so the dendrogram is the same tree with relabelled leaves): spatial neighbours become index neighbours
+        # and the sequential union-find / condensed-tree walk stays in cache; labels come back per rank.
+        rank = torch.empty(n, dtype=torch.int32, device=dev)
+        check(lib.pgs_hdb_morton_rank(ptr(scratch), n, D, ptr(rank), stream_ptr()))
+        rl = rank.long()
         u_h = torch.empty(n - 1, dtype=torch.int32, pin_memory=True)
         v_h = torch.empty(n - 1, dtype=torch.int32, pin_memory=True)
         w_h = torch.empty(n - 1, dtype=torch.float64, pin_memory=True)
-        u_h.copy_(u, non_blocking=True)
-        v_h.copy_(v, non_blocking=True)
+        u_h.copy_(rank[u.long()], non_blocking=True)
+        v_h.copy_(rank[v.long()], non_blocking=True)
         w_h.copy_(w, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        labels_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        labels_r = torch.empty(n, dtype=torch.int32, pin_memory=True)
         ncl = np.zeros(1, np.int32)
         with _lib.nvtx_range("pgs.hdbscan.tree_host"):
             check(lib.pgs_hdb_labels_host(u_h.data_ptr(), v_h.data_ptr(), w_h.data_ptr(), n, self.min_cluster_size,
-                                          self.cluster_selection_epsilon, labels_h.data_ptr(), ncl.ctypes.data))
+                                          self.cluster_selection_epsilon, labels_r.data_ptr(), ncl.ctypes.data))
+        labels_d = labels_r.to(dev, non_blocking=True)[rl]            # label of input row i = label of its rank
         self.core_distances_ = core
         self.mst_ = (u, v, w)
         self.n_clusters_ = int(ncl[0])
-        return labels_h
+        return labels_d
 
     def fit(self, X, y=None):
         self.fit_predict(X)
@@ -107,11 +113,11 @@ class HDBSCAN:
             Xt = X.detach().to(torch.float32).contiguous()
         if Xt.dim() != 2:
             raise ValueError("X must be [n_samples, n_features]")
-        labels_h = self._run(Xt)
+        labels_d = self._run(Xt)
         if as_numpy:
-            self.labels_ = labels_h.numpy().astype(np.int64)
+            self.labels_ = labels_d.cpu().numpy().astype(np.int64)
         else:
-            self.labels_ = labels_h.to(Xt.device, non_blocking=True).long()
+            self.labels_ = labels_d.long()
         return self.labels_
 
 

@@ -41,7 +41,16 @@ for rep in range(3):
     check(lib.pgs_hdb_labels_host(u_h.data_ptr(), v_h.data_ptr(), w_h.data_ptr(), n, 15, 0.006, labels_h.data_ptr(), ncl.ctypes.data))
     t_tree = time.perf_counter() - t
     t = time.perf_counter(); lab = labels_h.to(dev).long(); torch.cuda.synchronize(); t_h2d = time.perf_counter() - t
-    res["rep%d" % rep] = {"mst_ms": t_mst * 1e3, "pinned_alloc_ms": t_alloc * 1e3, "d2h_ms": t_d2h * 1e3, "tree_host_ms": t_tree * 1e3,
+    # the same stage on Morton-rank endpoints (what hdbscan.py does): same tree, cache-local leaves
+    rank = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib.pgs_hdb_morton_rank(ptr(scratch), n, D, ptr(rank), stream_ptr()))
+    ur = rank[u.long()].cpu().pin_memory(); vr = rank[v.long()].cpu().pin_memory()
+    labels_r = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    t = time.perf_counter()
+    check(lib.pgs_hdb_labels_host(ur.data_ptr(), vr.data_ptr(), w_h.data_ptr(), n, 15, 0.006, labels_r.data_ptr(), ncl.ctypes.data))
+    t_tree_rank = time.perf_counter() - t
+    same = bool(torch.equal(labels_r.to(dev)[rank.long()].long(), lab))
+    res["rep%d" % rep] = {"mst_ms": t_mst * 1e3, "pinned_alloc_ms": t_alloc * 1e3, "d2h_ms": t_d2h * 1e3, "tree_host_ms": t_tree * 1e3, "tree_host_morton_rank_ms": t_tree_rank * 1e3, "same_labels": same,
                           "labels_h2d_ms": t_h2d * 1e3, "rounds": int(rounds[0]), "clusters": int(ncl[0])}
 st = np.zeros((16, 4), np.int64)
 check(lib.pgs_hdb_search_stats(st.ctypes.data, 16))
