@@ -73,6 +73,11 @@ class FlatGradBucket:
                 p.grad = v
 
     def all_reduce_mean(self, world=None):
+        # weight-gradient kernels may still be running on the side stream (me.DW_DIRECT / fastpath.DW_SIDE_STREAM): whoever
+        # consumes the bucket waits for them first
+        if self.flat.is_cuda:
+            from . import me
+            me.join_side_stream()
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(dist.get_world_size() if world is None else world)
