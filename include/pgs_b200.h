@@ -158,14 +158,18 @@ int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, c
 int pgs_conv_prep_weights_batch(const int64_t* desc, int32_t n_desc, int64_t max_elems, void* stream);
 
 /* dW must be zeroed by the caller (accumulates).  in_idx/out_idx/offs (device) from pgs_kmap_pairs
- * of the FORWARD table; max_pairs = max_k (offs[k+1]-offs[k]) (host value, sizes the grid).
+ * of the FORWARD table (out_idx ascending within an offset); max_pairs >= max_k (offs[k+1]-offs[k]) -- the row count
+ * of the output side is what callers pass (host value, sizes the grid: the tensor-core kernel walks the output rows in
+ * blocks of 4096 with the kernel offset as the fastest grid index, so a block's X / dY rows stay in L2 across the
+ * offsets; rows beyond max_pairs fall into the last block).
  * in_idx == out_idx == offs == NULL: K == 1 identity pairs 0..max_pairs-1. */
 int pgs_conv_bwd_weight(const float* X, const float* dY,
                         const int32_t* in_idx, const int32_t* out_idx, const int32_t* offs,
                         int64_t max_pairs, int32_t K, int32_t c_in, int32_t c_out, int32_t mirror,
                         float* dW, void* stream);
 
-/* Tensor-core weight gradient (mma.sync tf32, 3-product split, pair rows loaded straight into the fragments);
+/* Tensor-core weight gradient (mma.sync tf32 + bf16 correction, pair rows loaded straight into the fragments with one
+ * vector load per lane and row piece);
  * pgs_conv_bwd_weight forwards to it when both channel counts are multiples of 16 (PGS_DW_IMPL=ffma disables). */
 int pgs_conv_dw_mma_supported(int32_t c_in, int32_t c_out);
 int pgs_conv_bwd_weight_mma(const float* X, const float* dY,
@@ -326,9 +330,13 @@ int pgs_bn_forward_ex(const float* X, int64_t n, int32_t C, const float* weight,
                       float* running_mean, float* running_var, int32_t training, float momentum, float eps,
                       int32_t relu, int32_t flags, double* sums, float* save_mean, float* save_invstd, float* Y,
                       void* stream);
+/* backward_ex: with relu != 0 and Y == NULL the mask [y > 0] is recomputed from X (y = fma(x, invstd * w, bias - mean *
+ * invstd * w) with the forward's own roundings), which saves reading Y; `bias` is the forward's bias (NULL = 0) and is
+ * only used for that. */
 int pgs_bn_backward_ex(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
-                       const float* save_mean, const float* save_invstd, int32_t training, int32_t relu,
-                       int32_t flags, double* sums, float* dX, float* dweight, float* dbias, void* stream);
+                       const float* bias, const float* save_mean, const float* save_invstd, int32_t training,
+                       int32_t relu, int32_t flags, double* sums, float* dX, float* dweight, float* dbias,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Feature-matrix glue of the U-Net (replaces `a + b` and ME.cat on SparseTensors sharing a coordinate map;

@@ -80,8 +80,8 @@ SIGNATURES = {
     "pgs_conv_prep_weights_batch": (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
     "pgs_bn_forward_ex": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                   c_float, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "pgs_bn_backward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
-                                   c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pgs_bn_backward_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pgs_add2": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "pgs_cat2": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
     "pgs_unet_record_bytes": (None, [c_void_p]),

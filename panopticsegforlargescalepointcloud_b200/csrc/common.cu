@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pgs {
@@ -124,6 +126,15 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* scratch
   count_launch(3);
   PGS_CHECK_LAUNCH();
   return PGS_OK;
+}
+
+int tc_corr16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PGS_TC_CORR");
+    v = (e && e[0] == 't') ? 0 : 1;
+  }
+  return v;
 }
 
 }  // namespace pgs

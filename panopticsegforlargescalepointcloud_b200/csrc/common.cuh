@@ -68,6 +68,10 @@ __host__ __device__ inline int floor_div(int a, int b) {  // b > 0
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// tcgen05 conv: 1 = the lo*hi + hi*lo correction products run as ONE bf16 MMA per 8 channels (default), 0 = as two
+// tf32 MMAs (PGS_TC_CORR=tf32); decides the layout of the arranged weights, so prep and kernel ask the same function
+int tc_corr16();
+
 // exclusive scan of int32 flags/counts (device-wide, 3 launches); out has n+1 entries,
 // out[n] = total.  scratch: scan_scratch_bytes(n).
 size_t scan_scratch_bytes(int64_t n);

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) conv_mma_prep_weights_kernel(const float*
 
 // All weight re-arrangements of a pass in ONE launch: blockIdx.y = descriptor (8 x int64: W, dst, K, C, N,
 // w_transposed, layout (0 = tcgen05, 1 = mma fragments), unused)
-__global__ void __launch_bounds__(256) conv_prep_batch_kernel(const int64_t* __restrict__ desc) {
+__global__ void __launch_bounds__(256) conv_prep_batch_kernel(const int64_t* __restrict__ desc, int tc_corr16) {
   const int64_t* d = desc + 8 * (int64_t)blockIdx.y;
   const float* W = (const float*)d[0];
   float* dst = (float*)d[1];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) conv_prep_batch_kernel(const int64_t* __r
   if (layout == 0) {
     const int64_t total = 2 * (int64_t)K * C * N;   // hi + lo planes (conv_prep.cuh)
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-      dst[e] = prep_tc_elem(W, K, C, N, wt, e);
+      dst[e] = prep_tc_elem(W, K, C, N, wt, tc_corr16, e);
   } else {
     const int64_t total = (int64_t)K * (C / 8) * (N / 8) * 32;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
@@ -674,7 +674,7 @@ int pgs_conv_prep_weights_batch(const int64_t* desc, int32_t n_desc, int64_t max
   PGS_CHECK_ARG(desc != nullptr && max_elems > 0, "bad descriptor table");
   int gx = (int)((max_elems + 255) / 256);
   if (gx > 64) gx = 64;
-  conv_prep_batch_kernel<<<dim3(gx, n_desc), 256, 0, (cudaStream_t)stream>>>(desc);
+  conv_prep_batch_kernel<<<dim3(gx, n_desc), 256, 0, (cudaStream_t)stream>>>(desc, tc_corr16());
   count_launch();
   PGS_CHECK_LAUNCH();
   return PGS_OK;

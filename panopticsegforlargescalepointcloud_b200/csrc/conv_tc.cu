@@ -23,8 +23,11 @@
 // is to feed A from tensor memory (TS mode, floor M*N/256 cycles).
 //
 // Precision: the parity bar is 1e-4 against an fp32 oracle; single-pass tf32 (10-bit mantissa) cannot meet
-// it, so operands are split a = hi + lo (hi = rn_tf32(a), lo = rn_tf32(a - hi)) on the way into shared memory
-// and three MMAs accumulate hi*hi + hi*lo + lo*hi into the same TMEM tile (error ~2^-21 per product).
+// it, so operands are split a = hi + lo (hi = rn_tf32(a)) on the way into shared memory: hi*hi accumulates in one
+// TMEM tile (tf32 MMA), the correction lo*hi + hi*lo in a second one -- as ONE bf16 K = 16 MMA per 8 channels whose
+// 16 contraction slots are [x_lo x 4 | x_hi x 4] . [w_hi x 4 | w_lo x 4] twice (error ~2^-20 per product; the
+// kernel is MMA-issue bound, so 2 instead of 3 MMAs per 8 channels is the lever; PGS_TC_CORR=tf32 selects the older
+// two-tf32-MMA correction).
 #include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint)
 
 #include <cstdlib>
@@ -96,6 +99,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with bf16 operands (K = 16 per instruction = the same 32 bytes per operand row as a tf32 K = 8 MMA)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -120,6 +135,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with a/b_format BF16 (1)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // round-to-nearest-even to tf32 (low 13 mantissa bits cleared) with integer ops: cvt.rna.tf32.f32 runs on the
 // slow conversion pipe (clock64 trace: 370 cycles per step for 32 conversions per thread), these run at full
@@ -143,6 +162,24 @@ __device__ __forceinline__ void split_store(float4 v, float4* hi_dst, float4* lo
   *hi_dst = h;
   *lo_dst = l;
 }
+// bf16-correction form: hi as above; the second 16 bytes are the 8 bf16 contraction slots [lo x 4 | hi x 4] of the
+// correction MMA (they meet [w_hi x 4 | w_lo x 4] of the same channels, conv_prep.cuh).  lo*hi + hi*lo is 2^-11 of the
+// main product, so 8 mantissa bits keep every term's error at the 2^-20 level of the dropped lo*lo product (the
+// mma.sync kernels use the same split, conv_mma.cu:mma_corr).
+__device__ __forceinline__ void split_store16(float4 v, float4* hi_dst, float4* corr_dst) {
+  float4 h;
+  h.x = to_tf32_rn(v.x);
+  h.y = to_tf32_rn(v.y);
+  h.z = to_tf32_rn(v.z);
+  h.w = to_tf32_rn(v.w);
+  uint4 c;
+  c.x = prep_pack_bf16(__float_as_uint(v.x - h.x), __float_as_uint(v.y - h.y));
+  c.y = prep_pack_bf16(__float_as_uint(v.z - h.z), __float_as_uint(v.w - h.w));
+  c.z = prep_pack_bf16(__float_as_uint(h.x), __float_as_uint(h.y));
+  c.w = prep_pack_bf16(__float_as_uint(h.z), __float_as_uint(h.w));
+  *hi_dst = h;
+  *(uint4*)corr_dst = c;
+}
 
 // ---------------------------------------------------------------------------------------------
 // weight pre-arrangement:  Wp[k][j][plane][q][n][4] = split_plane(B_k[n][j*16 + q*4 .. +3])   with  B_k = W[k]^T
@@ -150,12 +187,12 @@ __device__ __forceinline__ void split_store(float4 v, float4* hi_dst, float4* lo
 // plane 0 = tf32 hi, plane 1 = tf32 lo (conv_prep.cuh).  One (k, j) chunk = 128 * N contiguous bytes = one TMA box.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_tc_prep_weights_kernel(const float* __restrict__ W, int K, int c_in,
-                                                                    int c_out, int w_transposed,
+                                                                    int c_out, int w_transposed, int corr16,
                                                                     float* __restrict__ Wp) {
   // kernel-side naming: contraction length C (= c_in of the launch), N output channels (= c_out of the launch)
   const int64_t total = 2 * (int64_t)K * c_in * c_out;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    Wp[e] = prep_tc_elem(W, K, c_in, c_out, w_transposed, e);
+    Wp[e] = prep_tc_elem(W, K, c_in, c_out, w_transposed, corr16, e);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,8 +207,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
                                                               const __grid_constant__ CUtensorMap w_map,
                                                               const int32_t* __restrict__ nbr, int64_t n_q, int K,
                                                               int c_in, int c_out, int mirror, uint32_t tmem_cols,
-                                                              int ksplit, int bring, const int32_t* __restrict__ order,
-                                                              float* __restrict__ Y) {
+                                                              int ksplit, int bring, int corr16,
+                                                              const int32_t* __restrict__ order, float* __restrict__ Y) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_empty[kTcStages];
   __shared__ uint64_t bar_full[kTcMaxBRing];
@@ -204,7 +241,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t idesc = make_idesc_tf32(kTcM, N);
+  const uint32_t idesc = make_idesc_tf32(kTcM, N), idesc16 = make_idesc_bf16(kTcM, N);
   const int J = c_in / kTcKC;
 
   // rulebook columns of this tile for all offsets at once; which offsets have any neighbour in the tile
@@ -288,8 +325,13 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
         if (tid == 0 && it + look < total) request_weights(it + look);
         float4* Ahi = (float4*)st;
         float4* Alo = (float4*)(st + a_bytes);
-        split_store(qa0[p], &Ahi[g_q * kTcM + g_r0], &Alo[g_q * kTcM + g_r0]);
-        split_store(qa1[p], &Ahi[g_q * kTcM + g_r1], &Alo[g_q * kTcM + g_r1]);
+        if (corr16) {
+          split_store16(qa0[p], &Ahi[g_q * kTcM + g_r0], &Alo[g_q * kTcM + g_r0]);
+          split_store16(qa1[p], &Ahi[g_q * kTcM + g_r1], &Alo[g_q * kTcM + g_r1]);
+        } else {
+          split_store(qa0[p], &Ahi[g_q * kTcM + g_r0], &Alo[g_q * kTcM + g_r0]);
+          split_store(qa1[p], &Ahi[g_q * kTcM + g_r1], &Alo[g_q * kTcM + g_r1]);
+        }
         if (it + kTcPrefetch < total) load_step(it + kTcPrefetch, qa0[p], qa1[p]);   // refill the queue slot
         fence_proxy_async();
         __syncthreads();
@@ -310,8 +352,12 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const float* __rest
             // accumulator add inside the tensor core truncates, so fewer adds into the large sum = less bias
             const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
             umma_tf32(tmem_base, ahi, bhi, idesc, first);
-            umma_tf32(tmem_base + (uint32_t)N, alo, bhi, idesc, first);
-            umma_tf32(tmem_base + (uint32_t)N, ahi, blo, idesc, 1u);
+            if (corr16) {   // [x_lo | x_hi] . [w_hi | w_lo] of these 8 channels in one K = 16 bf16 MMA
+              umma_bf16(tmem_base + (uint32_t)N, alo, blo, idesc16, first);
+            } else {
+              umma_tf32(tmem_base + (uint32_t)N, alo, bhi, idesc, first);
+              umma_tf32(tmem_base + (uint32_t)N, ahi, blo, idesc, 1u);
+            }
           }
           umma_commit(&bar_empty[s]);
         }
@@ -427,7 +473,7 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const in
   int pg = (int)((total + 255) / 256);
   if (pg > kNumSM * 8) pg = kNumSM * 8;
   if (W != nullptr)   // W == NULL: scratch already holds the arranged weights (pgs_conv_prep_weights_batch)
-    conv_tc_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, Wp);
+    conv_tc_prep_weights_kernel<<<pg, 256, 0, s>>>(W, K, c_in, c_out, w_transposed, tc_corr16(), Wp);
   // tensor map of the arranged weights: [K * J * N/2 rows][64 floats], one box = N/2 rows = the 128*N-byte (k, j) chunk
   CUtensorMap w_map;
   {
@@ -466,7 +512,8 @@ int pgs_conv_fwd_tc(const float* X, const float* W, const int32_t* nbr, const in
   }
   if (ksplit > 1) PGS_CUDA(cudaMemsetAsync(Y, 0, (size_t)n_q * c_out * sizeof(float), s));
   const dim3 grid(gx, ksplit);
-  conv_tc_kernel<<<grid, kTcThreads, smem, s>>>(X, w_map, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, bring, order, Y);
+  conv_tc_kernel<<<grid, kTcThreads, smem, s>>>(X, w_map, nbr, n_q, K, c_in, c_out, mirror, cols, ksplit, bring,
+                                                tc_corr16(), order, Y);
   count_launch(W != nullptr ? 2 : 1);
   PGS_CHECK_LAUNCH();
   return PGS_OK;

@@ -16,34 +16,54 @@
 namespace pgs {
 
 constexpr int kBnThreads = 256;
-constexpr int kBnRowsPerBlock = 512;
+constexpr int kBnUnroll = 8;            // rows a thread has in flight in the reduction kernels
+constexpr int kBnMaxRowsPerThread = 32;   // fp32 partial sums never run over more rows than this
+
+// scale / shift of the normalise + affine step; spelled with explicit roundings because the backward kernels
+// recompute the ReLU mask [y > 0] from x and must land on the forward's bits
+__device__ __forceinline__ void bn_scale_shift(float mean, float invstd, float w, float b, float& scale, float& shift) {
+  scale = __fmul_rn(invstd, w);
+  shift = __fsub_rn(b, __fmul_rn(__fmul_rn(mean, invstd), w));
+}
+__device__ __forceinline__ float bn_affine(float x, float scale, float shift) { return __fmaf_rn(x, scale, shift); }
 
 // Thread block for the two reduction kernels: x <-> channel quad (C / 4 threads, so a thread always sees the
 // same four channels and a row is one coalesced C*4-byte read), y <-> row slot (floor(256 / (C/4)) rows side by
-// side).  Per-thread fp32 partials over <= kBnRowsPerBlock / rows_y rows, summed over y through shared memory,
-// then ONE fp64 atomicAdd per channel and block.
+// side).  A block owns rows_per_block = rows_per_thread * blockDim.y rows; a thread keeps kBnUnroll row loads in
+// flight, sums its <= 32 rows in fp32, the block sums the row slots in fp64 through shared memory, then ONE fp64
+// atomicAdd per channel and block.  (Round 2: 8 rows per thread and one load in flight ran these two kernels at
+// ~2 TB/s; the block count is now chosen so that the grid still covers the SMs twice.)
 //
 // sums[0..C) = sum x, sums[C..2C) = sum x^2   (fp64, zeroed by the caller)
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __restrict__ X, int64_t n, int C,
-                                                               double* __restrict__ sums) {
+                                                               int rows_per_block, double* __restrict__ sums) {
   extern __shared__ float bn_sm[];   // [rows_y][2C]
   const int cq = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
-  const int64_t row_begin = (int64_t)blockIdx.x * kBnRowsPerBlock;
-  const int64_t row_end = (row_begin + kBnRowsPerBlock < n) ? row_begin + kBnRowsPerBlock : n;
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = (row_begin + rows_per_block < n) ? row_begin + rows_per_block : n;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  for (int64_t r = row_begin + ry; r < row_end; r += R) {
-    const float4 v = __ldg((const float4*)(X + r * C) + cq);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+  for (int64_t r = row_begin + ry; r < row_end; r += (int64_t)R * kBnUnroll) {
+    float4 v[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      v[u] = (rr < row_end) ? __ldg((const float4*)(X + rr * C) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+      q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y);
+      q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+    }
   }
   float* mine = bn_sm + (size_t)ry * 2 * C;
   *(float4*)&mine[4 * cq] = s;
   *(float4*)&mine[C + 4 * cq] = q;
   __syncthreads();
   for (int i = ry * blockDim.x + cq; i < 2 * C; i += blockDim.x * R) {
-    float t = 0.f;
-    for (int y = 0; y < R; ++y) t += bn_sm[(size_t)y * 2 * C + i];
-    atomicAdd(&sums[i], (double)t);
+    double t = 0.0;
+    for (int y = 0; y < R; ++y) t += (double)bn_sm[(size_t)y * 2 * C + i];
+    atomicAdd(&sums[i], t);
   }
 }
 
@@ -79,9 +99,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
         save_invstd[c] = invstd;
       }
     }
-    const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
-    bn_sm[c] = invstd * w;
-    bn_sm[C + c] = b - mean * invstd * w;
+    bn_scale_shift(mean, invstd, weight ? weight[c] : 1.f, bias ? bias[c] : 0.f, bn_sm[c], bn_sm[C + c]);
   }
   __syncthreads();
   const int c4 = C / 4;
@@ -90,10 +108,10 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
     const int cq = (int)(e % c4);
     const float4 v = __ldg((const float4*)X + e);
     float4 y;
-    y.x = fmaf(v.x, bn_sm[4 * cq + 0], bn_sm[C + 4 * cq + 0]);
-    y.y = fmaf(v.y, bn_sm[4 * cq + 1], bn_sm[C + 4 * cq + 1]);
-    y.z = fmaf(v.z, bn_sm[4 * cq + 2], bn_sm[C + 4 * cq + 2]);
-    y.w = fmaf(v.w, bn_sm[4 * cq + 3], bn_sm[C + 4 * cq + 3]);
+    y.x = bn_affine(v.x, bn_sm[4 * cq + 0], bn_sm[C + 4 * cq + 0]);
+    y.y = bn_affine(v.y, bn_sm[4 * cq + 1], bn_sm[C + 4 * cq + 1]);
+    y.z = bn_affine(v.z, bn_sm[4 * cq + 2], bn_sm[C + 4 * cq + 2]);
+    y.w = bn_affine(v.w, bn_sm[4 * cq + 3], bn_sm[C + 4 * cq + 3]);
     if (relu) {
       y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
     }
@@ -101,38 +119,64 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(
   }
 }
 
-// sums[0..C) = sum g, sums[C..2C) = sum g * xhat,  g = dY * [Y > 0] (relu) or dY   (same block shape as bn_stats)
+// sums[0..C) = sum g, sums[C..2C) = sum g * xhat,  g = dY * [y > 0] (relu) or dY   (same block shape as bn_stats).
+// The mask comes from the forward output Y when the caller passes it, else it is recomputed from x (one array less
+// to read: y = fma(x, scale, shift) with the forward's own roundings).
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_stats_kernel(
     const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ dY, int64_t n, int C,
-    const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int relu, double* __restrict__ sums) {
+    const float* __restrict__ save_mean, const float* __restrict__ save_invstd, const float* __restrict__ weight,
+    const float* __restrict__ bias, int relu, int rows_per_block, double* __restrict__ sums) {
   extern __shared__ float bn_sm[];   // [rows_y][2C]
+  constexpr int UB = kBnUnroll / 2;
   const int cq = threadIdx.x, ry = threadIdx.y, R = blockDim.y;
   const float4 mean = *(const float4*)&save_mean[4 * cq];
   const float4 inv = *(const float4*)&save_invstd[4 * cq];
-  const int64_t row_begin = (int64_t)blockIdx.x * kBnRowsPerBlock;
-  const int64_t row_end = (row_begin + kBnRowsPerBlock < n) ? row_begin + kBnRowsPerBlock : n;
+  float sc[4], sh[4];
+  {
+    const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, iv[4] = {inv.x, inv.y, inv.z, inv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      bn_scale_shift(mv[j], iv[j], weight ? weight[4 * cq + j] : 1.f, bias ? bias[4 * cq + j] : 0.f, sc[j], sh[j]);
+  }
+  const bool mask_y = relu && Y != nullptr, mask_x = relu && Y == nullptr;
+  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t row_end = (row_begin + rows_per_block < n) ? row_begin + rows_per_block : n;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-  for (int64_t r = row_begin + ry; r < row_end; r += R) {
-    const float4 x = __ldg((const float4*)(X + r * C) + cq);
-    float4 g = __ldg((const float4*)(dY + r * C) + cq);
-    if (relu) {
-      const float4 y = __ldg((const float4*)(Y + r * C) + cq);
-      g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f; g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+  for (int64_t r = row_begin + ry; r < row_end; r += (int64_t)R * UB) {
+    float4 x[UB], g[UB], y[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int64_t rr = r + (int64_t)u * R;
+      const bool ok = rr < row_end;
+      x[u] = ok ? __ldg((const float4*)(X + rr * C) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[u] = ok ? __ldg((const float4*)(dY + rr * C) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mask_y) y[u] = ok ? __ldg((const float4*)(Y + rr * C) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-    q.x = fmaf(g.x, (x.x - mean.x) * inv.x, q.x);
-    q.y = fmaf(g.y, (x.y - mean.y) * inv.y, q.y);
-    q.z = fmaf(g.z, (x.z - mean.z) * inv.z, q.z);
-    q.w = fmaf(g.w, (x.w - mean.w) * inv.w, q.w);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (mask_x) {
+        y[u] = make_float4(bn_affine(x[u].x, sc[0], sh[0]), bn_affine(x[u].y, sc[1], sh[1]),
+                           bn_affine(x[u].z, sc[2], sh[2]), bn_affine(x[u].w, sc[3], sh[3]));
+      }
+      if (relu) {
+        g[u].x = y[u].x > 0.f ? g[u].x : 0.f; g[u].y = y[u].y > 0.f ? g[u].y : 0.f;
+        g[u].z = y[u].z > 0.f ? g[u].z : 0.f; g[u].w = y[u].w > 0.f ? g[u].w : 0.f;
+      }
+      s.x += g[u].x; s.y += g[u].y; s.z += g[u].z; s.w += g[u].w;
+      q.x = fmaf(g[u].x, (x[u].x - mean.x) * inv.x, q.x);
+      q.y = fmaf(g[u].y, (x[u].y - mean.y) * inv.y, q.y);
+      q.z = fmaf(g[u].z, (x[u].z - mean.z) * inv.z, q.z);
+      q.w = fmaf(g[u].w, (x[u].w - mean.w) * inv.w, q.w);
+    }
   }
   float* mine = bn_sm + (size_t)ry * 2 * C;
   *(float4*)&mine[4 * cq] = s;
   *(float4*)&mine[C + 4 * cq] = q;
   __syncthreads();
   for (int i = ry * blockDim.x + cq; i < 2 * C; i += blockDim.x * R) {
-    float t = 0.f;
-    for (int y = 0; y < R; ++y) t += bn_sm[(size_t)y * 2 * C + i];
-    atomicAdd(&sums[i], (double)t);
+    double t = 0.0;
+    for (int y = 0; y < R; ++y) t += (double)bn_sm[(size_t)y * 2 * C + i];
+    atomicAdd(&sums[i], t);
   }
 }
 
@@ -141,14 +185,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_stats_kernel(
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ dY, int64_t n, int C,
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, const float* __restrict__ weight,
-    const double* __restrict__ sums, int training, int relu, int accumulate, float* __restrict__ dX,
-    float* __restrict__ dweight, float* __restrict__ dbias) {
-  extern __shared__ float bn_sm[];   // [4][C]: mean, invstd * w, mean_g, mean_gh * invstd... see below
+    const float* __restrict__ bias, const double* __restrict__ sums, int training, int relu, int accumulate,
+    float* __restrict__ dX, float* __restrict__ dweight, float* __restrict__ dbias) {
+  extern __shared__ float bn_sm[];   // [7][C]
   float* a_mean = bn_sm;
   float* a_inv = bn_sm + C;
   float* a_k1 = bn_sm + 2 * C;   // w * invstd
   float* a_mg = bn_sm + 3 * C;   // mean(g)
   float* a_mgh = bn_sm + 4 * C;  // mean(g * xhat)
+  float* a_sc = bn_sm + 5 * C;   // forward scale / shift (ReLU mask from x)
+  float* a_sh = bn_sm + 6 * C;
   for (int c = threadIdx.x; c < C; c += kBnThreads) {
     const float w = weight ? weight[c] : 1.f;
     a_mean[c] = save_mean[c];
@@ -156,23 +202,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     a_k1[c] = w * save_invstd[c];
     a_mg[c] = training ? (float)(sums[c] / (double)n) : 0.f;
     a_mgh[c] = training ? (float)(sums[C + c] / (double)n) : 0.f;
+    bn_scale_shift(save_mean[c], save_invstd[c], w, bias ? bias[c] : 0.f, a_sc[c], a_sh[c]);
     if (blockIdx.x == 0) {
       if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)sums[c];
       if (dweight) dweight[c] = (accumulate ? dweight[c] : 0.f) + (float)sums[C + c];
     }
   }
   __syncthreads();
+  const bool mask_y = relu && Y != nullptr, mask_x = relu && Y == nullptr;
   const int c4 = C / 4;
   const int64_t total = n * c4;
   for (int64_t e = (int64_t)blockIdx.x * kBnThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kBnThreads) {
     const int cq = (int)(e % c4);
     const float4 x = __ldg((const float4*)X + e);
     float4 g = __ldg((const float4*)dY + e);
-    if (relu) {
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+    float gv[4] = {g.x, g.y, g.z, g.w};
+    if (mask_y) {
       const float4 y = __ldg((const float4*)Y + e);
-      g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f; g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f;
+      gv[0] = y.x > 0.f ? gv[0] : 0.f; gv[1] = y.y > 0.f ? gv[1] : 0.f;
+      gv[2] = y.z > 0.f ? gv[2] : 0.f; gv[3] = y.w > 0.f ? gv[3] : 0.f;
+    } else if (mask_x) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) gv[t] = bn_affine(xv[t], a_sc[4 * cq + t], a_sh[4 * cq + t]) > 0.f ? gv[t] : 0.f;
     }
-    const float xv[4] = {x.x, x.y, x.z, x.w}, gv[4] = {g.x, g.y, g.z, g.w};
     float o[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -212,6 +265,13 @@ __global__ void __launch_bounds__(256) cat2_kernel(float4* __restrict__ a, int c
   }
 }
 
+// rows per block of the reduction kernels: as many rows per thread as still leave >= 2 blocks per SM
+static inline int bn_rows_per_block(int64_t n, int rows_y) {
+  int rpt = kBnMaxRowsPerThread;
+  while (rpt > 4 && (n + (int64_t)rpt * rows_y - 1) / ((int64_t)rpt * rows_y) < 2 * kNumSM) rpt >>= 1;
+  return rpt * rows_y;
+}
+
 static inline int bn_apply_grid(int64_t total4) {
   int64_t g = (total4 + kBnThreads - 1) / kBnThreads;
   const int64_t cap = (int64_t)kNumSM * 8;
@@ -240,9 +300,10 @@ int pgs_bn_forward_ex(const float* X, int64_t n, int32_t C, const float* weight,
   cudaStream_t s = (cudaStream_t)stream;
   if (training) {
     if (!(flags & PGS_BN_SUMS_ZEROED)) PGS_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
-    const unsigned g = (unsigned)((n + kBnRowsPerBlock - 1) / kBnRowsPerBlock);
     const dim3 blk(C / 4, kBnThreads / (C / 4));
-    bn_stats_kernel<<<g, blk, (size_t)blk.y * 2 * C * sizeof(float), s>>>(X, n, C, sums);
+    const int rpb = bn_rows_per_block(n, blk.y);
+    const unsigned g = (unsigned)((n + rpb - 1) / rpb);
+    bn_stats_kernel<<<g, blk, (size_t)blk.y * 2 * C * sizeof(float), s>>>(X, n, C, rpb, sums);
     count_launch();
   }
   bn_apply_kernel<<<bn_apply_grid(n * (C / 4)), kBnThreads, 2 * C * sizeof(float), s>>>(
@@ -255,25 +316,27 @@ int pgs_bn_forward_ex(const float* X, int64_t n, int32_t C, const float* weight,
 int pgs_bn_backward(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
                     const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, double* sums,
                     float* dX, float* dweight, float* dbias, void* stream) {
-  return pgs_bn_backward_ex(X, Y, dY, n, C, weight, save_mean, save_invstd, training, relu, 0, sums, dX, dweight, dbias,
-                            stream);
+  PGS_CHECK_ARG(!relu || Y != nullptr, "the ReLU mask needs the forward output");
+  return pgs_bn_backward_ex(X, Y, dY, n, C, weight, nullptr, save_mean, save_invstd, training, relu, 0, sums, dX, dweight,
+                            dbias, stream);
 }
 
 int pgs_bn_backward_ex(const float* X, const float* Y, const float* dY, int64_t n, int32_t C, const float* weight,
-                       const float* save_mean, const float* save_invstd, int32_t training, int32_t relu, int32_t flags,
+                       const float* bias, const float* save_mean, const float* save_invstd, int32_t training, int32_t relu,
+                       int32_t flags,
                        double* sums, float* dX, float* dweight, float* dbias, void* stream) {
   PGS_CHECK_ARG(C >= 4 && C % 4 == 0 && C <= 1024, "channel count must be a multiple of 4, at most 1024");
-  PGS_CHECK_ARG(!relu || Y != nullptr, "the ReLU mask needs the forward output");
   if (n == 0) return PGS_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (!(flags & PGS_BN_SUMS_ZEROED)) PGS_CUDA(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), s));
-  const unsigned g = (unsigned)((n + kBnRowsPerBlock - 1) / kBnRowsPerBlock);
   const dim3 blk(C / 4, kBnThreads / (C / 4));
-  bn_bwd_stats_kernel<<<g, blk, (size_t)blk.y * 2 * C * sizeof(float), s>>>(X, Y, dY, n, C, save_mean, save_invstd, relu,
-                                                                          sums);
-  bn_bwd_apply_kernel<<<bn_apply_grid(n * (C / 4)), kBnThreads, 5 * C * sizeof(float), s>>>(
-      X, Y, dY, n, C, save_mean, save_invstd, weight, sums, training, relu, (flags & PGS_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0,
-      dX, dweight, dbias);
+  const int rpb = bn_rows_per_block(n, blk.y);
+  const unsigned g = (unsigned)((n + rpb - 1) / rpb);
+  bn_bwd_stats_kernel<<<g, blk, (size_t)blk.y * 2 * C * sizeof(float), s>>>(X, Y, dY, n, C, save_mean, save_invstd, weight,
+                                                                          bias, relu, rpb, sums);
+  bn_bwd_apply_kernel<<<bn_apply_grid(n * (C / 4)), kBnThreads, 7 * C * sizeof(float), s>>>(
+      X, Y, dY, n, C, save_mean, save_invstd, weight, bias, sums, training, relu,
+      (flags & PGS_BN_ACCUMULATE_PARAM_GRADS) ? 1 : 0, dX, dweight, dbias);
   count_launch(2);
   PGS_CHECK_LAUNCH();
   return PGS_OK;

@@ -7,6 +7,7 @@
 // autograd's reverse walk over the same graph.
 #include <nvtx3/nvToolsExt.h>   // header-only; ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -186,8 +187,11 @@ int pgs_unet_backward(const pgs_unet_op* ops, int32_t n_ops, int32_t n_slots, in
         PGS_CHECK_ARG(used + na <= garena_elems, "gradient arena too small");
         float* dx = take(na);
         const int flags = PGS_BN_SUMS_ZEROED | (b.accumulate ? PGS_BN_ACCUMULATE_PARAM_GRADS : 0);
-        rc = pgs_bn_backward_ex(slot_ptr[a], op.relu ? slot_ptr[d] : nullptr, g, slot_n[a], C, b.weight, stats + so,
-                                stats + so + C, b.training, op.relu, flags, sums + so, dx, b.dweight, b.dbias, stream);
+        // Y = NULL: the ReLU mask is recomputed from x (one array less to read); PGS_BN_MASK=y reads it from Y
+        static const bool mask_from_y = [] { const char* e = getenv("PGS_BN_MASK"); return e && e[0] == 'y'; }();
+        rc = pgs_bn_backward_ex(slot_ptr[a], (op.relu && mask_from_y) ? slot_ptr[d] : nullptr, g, slot_n[a], C, b.weight,
+                                b.bias, stats + so, stats + so + C,
+                                b.training, op.relu, flags, sums + so, dx, b.dweight, b.dbias, stream);
         glist[a].push_back(dx);
         break;
       }

@@ -509,7 +509,7 @@ class _UNetFn(torch.autograd.Function):
                 flags = BN_ZEROED | (BN_ACC if (direct[iw] or direct[ib]) else 0)
                 if direct[iw] != direct[ib] and needs[iw] and needs[ib]:
                     raise RuntimeError("batch-norm weight and bias must both have (or both lack) a .grad buffer")
-                rc = lib.pgs_bn_backward_ex(ptrs[a], ptrs[dst] if relu else None, g, n[a], Cb, params[iw].data_ptr(),
+                rc = lib.pgs_bn_backward_ex(ptrs[a], None, g, n[a], Cb, params[iw].data_ptr(), params[ib].data_ptr(),
                                             stats_p + 4 * soff[idx], stats_p + 4 * (soff[idx] + Cb), int(training[idx]),
                                             int(relu), flags, sums_p + 8 * soff[idx], dx, pgrad(iw), pgrad(ib), sp)
                 if rc:

@@ -9,8 +9,9 @@ from panopticsegforlargescalepointcloud_b200._lib import ptr, check, stream_ptr
 dev = torch.device("cuda:0")
 lib = _lib.load()
 N = 200000
-s = scenes.make_scene("urban", N, 0.12, 16.0, seed=0)
-coords = np.concatenate([np.zeros((N, 1), np.int32), s.coords], 1)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4      # cylinders in the batch (bench.py's step has 4)
+coords = np.concatenate([np.concatenate([np.full((N, 1), b, np.int32), scenes.make_scene("urban", N, 0.12, 16.0, seed=b).coords], 1)
+                         for b in range(B)], 0)
 mgr = me.CoordinateManager(torch.from_numpy(coords).to(dev))
 kms = {0: mgr.kernel_map(1, 1, 1, 1, 3)}
 mgr.stride(1, 2); kms[1] = mgr.kernel_map(2, 2, 2, 1, 3)

@@ -41,7 +41,7 @@ def test_bn_ex_flags(cuda_device):
     X = torch.randn(n, C, generator=g).to(cuda_device); dY = torch.randn(n, C, generator=g).to(cuda_device)
     w = (torch.rand(C, generator=g) + 0.5).to(cuda_device); b = torch.randn(C, generator=g).to(cuda_device)
 
-    def run(flags, pre):
+    def run(flags, pre, mask_from_x=False):
         rm, rv = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
         Y, dX = torch.empty_like(X), torch.empty_like(X)
         st = torch.empty(2, C, device=cuda_device)
@@ -52,8 +52,8 @@ def test_bn_ex_flags(cuda_device):
         if flags & 2:
             sums.zero_()
         dwb = torch.full((2, C), pre, device=cuda_device)
-        L.check(lib.pgs_bn_backward_ex(P(X), P(Y), P(dY), n, C, P(w), P(st[0]), P(st[1]), 1, 1, flags, P(sums), P(dX),
-                                       P(dwb[0]), P(dwb[1]), S()))
+        L.check(lib.pgs_bn_backward_ex(P(X), None if mask_from_x else P(Y), P(dY), n, C, P(w), P(b), P(st[0]), P(st[1]), 1,
+                                       1, flags, P(sums), P(dX), P(dwb[0]), P(dwb[1]), S()))
         return Y, dX, dwb, rm, rv
 
     Y0, dX0, g0, rm0, rv0 = run(0, 123.0)          # plain: memsets inside, gradients overwritten
@@ -61,6 +61,10 @@ def test_bn_ex_flags(cuda_device):
     assert torch.equal(Y0, Y1) and torch.equal(rm0, rm1) and torch.equal(rv0, rv1)
     assert torch.allclose(dX0, dX1, rtol=0, atol=1e-6)
     assert torch.allclose(g1, g0 + 2.5, rtol=1e-6, atol=1e-5)
+    # Y == NULL: the ReLU mask is recomputed from x with the forward's roundings -> the same mask, bit for bit
+    Y2, dX2, g2, _, _ = run(0, 123.0, mask_from_x=True)
+    # (a flipped mask bit would change dX by ~|dY| w invstd; 1e-6 only allows for the order of the fp64 atomics)
+    assert torch.allclose(dX2, dX0, rtol=0, atol=1e-6) and torch.allclose(g2, g0, rtol=1e-6, atol=1e-5)
     Xr = X.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
     ref = torch.relu(torch.nn.functional.batch_norm(Xr, None, None, wr, br, True, 0.1, 1e-5))
     ref.backward(dY)
