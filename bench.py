@@ -65,21 +65,6 @@ def make_inputs(seeds, n=N_POINTS, kind="urban", grid=GRID, radius=RADIUS):
         seeds = [seeds]
     ss = [scenes.make_scene(kind, n, grid, radius, seed=s) for s in seeds]
     heads = [scenes.synthetic_head_outputs(s, seed=sd) for s, sd in zip(ss, seeds)]
-    order = os.environ.get("PGS_BENCH_ORDER")          # experiment: point order of the input ("morton" / "raster")
-    if order:
-        for i, (s, h) in enumerate(zip(ss, heads)):
-            c = (s.coords - s.coords.min(0)).astype(np.int64)
-            if order == "morton":
-                key = np.zeros(len(c), np.int64)
-                for b in range(16):
-                    for a in range(3):
-                        key |= ((c[:, a] >> b) & 1) << (3 * b + a)
-            else:
-                key = (c[:, 2] << 32) | (c[:, 1] << 16) | c[:, 0]
-            perm = np.argsort(key, kind="stable")
-            for k in ("pos", "coords", "x", "y", "instance_mask", "vote_label", "instance_labels"):
-                setattr(s, k, getattr(s, k)[perm])
-            heads[i] = tuple(a[perm] for a in h)
     b = scenes.collate(ss)
     b.syn_shifted = np.concatenate([s.pos + h[0] for s, h in zip(ss, heads)]).astype(np.float32)
     b.syn_embed = np.concatenate([h[1] for h in heads]).astype(np.float32)

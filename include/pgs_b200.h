@@ -117,6 +117,7 @@ int pgs_conv_fwd(const float* X, const float* W, const int32_t* nbr, int64_t n_q
  * pgs_kmap_permute writes nbr_sorted[k][r] = nbr[k][order[r]].  Passing (nbr_sorted, order) to a tensor-core entry
  * point gives the same rows as (nbr, NULL): tile row r is output row order[r]. */
 int pgs_kmap_row_masks(const int32_t* nbr, int64_t n_q, int32_t K, int32_t* masks, void* stream);
+
 int pgs_kmap_permute(const int32_t* nbr, int64_t n_q, int32_t K, const int32_t* order, int32_t* nbr_sorted,
                      void* stream);
 
@@ -158,10 +159,8 @@ int pgs_conv_fwd_mma_split(const float* X, const float* W, const int32_t* nbr, c
 int pgs_conv_prep_weights_batch(const int64_t* desc, int32_t n_desc, int64_t max_elems, void* stream);
 
 /* dW must be zeroed by the caller (accumulates).  in_idx/out_idx/offs (device) from pgs_kmap_pairs
- * of the FORWARD table (out_idx ascending within an offset); max_pairs >= max_k (offs[k+1]-offs[k]) -- the row count
- * of the output side is what callers pass (host value, sizes the grid: the tensor-core kernel walks the output rows in
- * blocks of 4096 with the kernel offset as the fastest grid index, so a block's X / dY rows stay in L2 across the
- * offsets; rows beyond max_pairs fall into the last block).
+ * of the FORWARD table; max_pairs >= max_k (offs[k+1]-offs[k]) (host value, sizes the grid; callers pass the row count
+ * of the output side, which bounds it without a device read-back).
  * in_idx == out_idx == offs == NULL: K == 1 identity pairs 0..max_pairs-1. */
 int pgs_conv_bwd_weight(const float* X, const float* dY,
                         const int32_t* in_idx, const int32_t* out_idx, const int32_t* offs,

@@ -19,8 +19,7 @@
 namespace pgs {
 
 constexpr int kDmThreads = 256;
-constexpr int kDmChunk = 1024;   // pairs staged at a time (indices in shared memory)
-constexpr int kDmRowBlock = 4096;   // output rows per CTA (all its pairs of one kernel offset)
+constexpr int kDmChunk = 1024;   // pairs per CTA (128 per warp)
 
 __device__ __forceinline__ void dm_split(float v, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(v) + 0x00001000u) & 0xFFFFE000u;   // round-half-up to tf32; the tensor core truncates lo
@@ -54,10 +53,11 @@ __device__ __forceinline__ void dm_corr(float (&d)[4], const uint32_t (&ahi)[4],
 // Row pieces of a pair arrive as ONE vector load per lane: lane (g, t) reads the 2 MT (A) / NT (B) consecutive
 // floats  X[in(p)][ci0 + 2 MT g ..]  /  dY[out(p)][co0 + NT g ..]  of its pairs p = t and t + 4, so the 8 lanes of a
 // pair cover one contiguous 64 MT / 32 NT-byte piece of the row and a warp-level load touches 4 rows (4 L1 wavefronts
-// moving 256 .. 512 bytes).  The scalar version this replaces (one 4-byte load per fragment register: 4 rows x 32
-// bytes per instruction, 8 instructions per 8 pairs at 16 x 16 and 16 at 32 x 32) was bound by exactly those
-// wavefronts -- ~2 cycles each in the L1 pipeline, 8 per pair at 32 x 32 -- not by L2 or HBM.  The tile's channels are
-// therefore permuted inside the MMA (dW is written back through the same permutation):
+// moving 256 .. 512 bytes) instead of one 4-byte load per fragment register (4 rows x 32 bytes per instruction, 8
+// instructions per 8 pairs at 16 x 16 and 16 at 32 x 32).  A quarter of the load instructions, the same time
+// (146 vs 150 us at 16 x 16 x 5.3 M pairs): the sectors, not the instructions, are the limit (see the kernel's
+// header).  The tile's channels are therefore permuted inside the MMA (dW is written back through the same
+// permutation):
 //     A m-tile m, fragment row g / g + 8   <->  input channel  ci0 + 2 MT g + 2 m / + 2 m + 1
 //     B n-tile n, fragment column g        <->  output channel co0 + NT g + n
 template <int NF>
@@ -78,42 +78,17 @@ __device__ __forceinline__ void dm_load(const float* __restrict__ p, bool ok, fl
   }
 }
 
-// lower bounds of v0 and v1 in the ascending array A[lo, hi), found by the whole CTA with 256-way probes (three
-// rounds for a million entries instead of twenty dependent loads of a binary search)
-__device__ __forceinline__ void dm_block_bounds(const int32_t* __restrict__ A, int lo, int hi, int v0, int v1, int& r0,
-                                                int& r1) {
-  int lo0 = lo, hi0 = hi, lo1 = lo, hi1 = hi;   // the answer lies in [lo, hi] (hi itself = "none smaller from here on")
-  while (hi0 > lo0 || hi1 > lo1) {   // block-uniform
-    const int s0 = (hi0 - lo0 + kDmThreads - 1) / kDmThreads, s1 = (hi1 - lo1 + kDmThreads - 1) / kDmThreads;
-    const int p0 = lo0 + (int)threadIdx.x * s0, p1 = lo1 + (int)threadIdx.x * s1;   // (< hi + 256 s: no overflow, positions < 2^30)
-    const int b0 = (p0 < hi0) ? (__ldg(&A[p0]) < v0) : 0;
-    const int b1 = (p1 < hi1) ? (__ldg(&A[p1]) < v1) : 0;
-    const int c0 = __syncthreads_count(b0), c1 = __syncthreads_count(b1);
-    if (hi0 > lo0) {
-      const int nh = lo0 + c0 * s0;
-      if (c0 == 0) hi0 = lo0;
-      else { lo0 += (c0 - 1) * s0 + 1; if (nh < hi0) hi0 = nh; }
-    }
-    if (hi1 > lo1) {
-      const int nh = lo1 + c1 * s1;
-      if (c1 == 0) hi1 = lo1;
-      else { lo1 += (c1 - 1) * s1 + 1; if (nh < hi1) hi1 = nh; }
-    }
-  }
-  r0 = lo0;
-  r1 = lo1;
-}
-
-// MT m-tiles of 16 input channels, NT n-tiles of 8 output channels per CTA tile.
-// Grid: x = kernel offset (fastest), y = channel tile, z = block of kDmRowBlock OUTPUT rows; a CTA takes the pairs of
-// its offset whose output row lies in its block (the pair list of an offset is ascending in the output row).  The 27
-// offsets of a row block run next to each other, so the X / dY rows of the block are read from HBM once and then hit
-// in L2 -- walking one offset after the other over all rows (the round-2 order) swept the 100+ MB of X, dY and pair
-// lists of a 800 k-row level through the 126 MB L2 twenty-seven times.
+// MT m-tiles of 16 input channels, NT n-tiles of 8 output channels per CTA tile; grid: x = chunk of kDmChunk pairs of
+// one kernel offset, y = channel tile, z = kernel offset.
+// (Tried and dropped, profiles/r2_dw_variants.json: walking the output rows in blocks of 4096 with the kernel offset
+// as the fastest grid index, so that a block's X / dY rows stay in L2 across the 27 offsets -- 0 .. 20 % SLOWER.  The
+// kernel is not waiting for HBM: it moves ~16 bytes per clock and SM of scattered 32-byte sectors from L2, 4.6 TB/s
+// over the chip, whatever the order, the load width or the math pipe -- the FFMA kernel takes the same time at
+// 16 x 16 -- which is the L2 -> SM bandwidth this access pattern gets.)
 template <int MT, int NT>
-__global__ void __launch_bounds__(kDmThreads, (MT * NT <= 4) ? 3 : 2) conv_dw_mma_kernel(
+__global__ void __launch_bounds__(kDmThreads) conv_dw_mma_kernel(
     const float* __restrict__ X, const float* __restrict__ dY, const int32_t* __restrict__ in_idx,
-    const int32_t* __restrict__ out_idx, const int32_t* __restrict__ offs, int64_t n_rows, int K, int mirror,
+    const int32_t* __restrict__ out_idx, const int32_t* __restrict__ offs, int64_t n_identity, int K, int mirror,
     int c_in, int c_out, int n_co_tiles, float* __restrict__ dW) {
   constexpr int TCI = 16 * MT, TCO = 8 * NT, AF = 2 * MT;
   __shared__ int s_in[kDmChunk], s_out[kDmChunk];
@@ -122,13 +97,17 @@ __global__ void __launch_bounds__(kDmThreads, (MT * NT <= 4) ? 3 : 2) conv_dw_mm
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int ci0 = (blockIdx.y / n_co_tiles) * TCI, co0 = (blockIdx.y % n_co_tiles) * TCO;
-  const int tk = blockIdx.x;
-  const int row_lo = (int)blockIdx.z * kDmRowBlock;   // (rows and pair positions fit 31 bits: offs is int32)
-  const int row_hi = (row_lo + kDmRowBlock < (int)n_rows) ? row_lo + kDmRowBlock : (int)n_rows;
-  int p_lo = row_lo, p_hi = row_hi;   // identity pairs (K == 1, no lists): pair p = row p
-  if (offs)   // the last block is open-ended: `n_rows` is the caller's bound on pairs per offset, rows may go beyond it
-    dm_block_bounds(out_idx, offs[tk], offs[tk + 1], row_lo, blockIdx.z + 1 == gridDim.z ? 0x7fffffff : row_hi, p_lo, p_hi);
-  if (p_lo >= p_hi) return;
+  const int tk = blockIdx.z;
+  const int64_t p_begin = offs ? offs[tk] : 0, p_end = offs ? offs[tk + 1] : n_identity;
+  const int64_t start = p_begin + (int64_t)blockIdx.x * kDmChunk;
+  if (start >= p_end) return;
+  const int n_pairs = (int)((p_end - start < kDmChunk) ? (p_end - start) : kDmChunk);
+  for (int i = tid; i < kDmChunk; i += kDmThreads) {
+    const bool ok = i < n_pairs;
+    s_in[i] = ok ? (in_idx ? __ldg(&in_idx[start + i]) : (int)(start + i)) : -1;
+    s_out[i] = ok ? (out_idx ? __ldg(&out_idx[start + i]) : (int)(start + i)) : -1;
+  }
+  __syncthreads();
 
   float accm[MT][NT][4], accc[MT][NT][4];
 #pragma unroll
@@ -138,58 +117,47 @@ __global__ void __launch_bounds__(kDmThreads, (MT * NT <= 4) ? 3 : 2) conv_dw_mm
 #pragma unroll
       for (int c = 0; c < 4; ++c) accm[m][n][c] = accc[m][n][c] = 0.f;
 
+  // warp w owns pairs [128 w, 128 w + 128) of the chunk: 16 contraction steps of 8 pairs
+  const int wbase = warp * (kDmChunk / (kDmThreads / 32));
   const float* Xc = X + ci0 + AF * g;
   const float* Dc = dY + co0 + NT * g;
-  // U contraction steps (8 pairs each) are loaded together before their MMAs (latency: index -> row -> mma)
+  // U contraction steps are loaded together before their MMAs (latency: index -> row -> mma)
   constexpr int U = (MT * NT <= 2) ? 4 : 2;
-  constexpr int W = kDmThreads / 32;
-  for (int start = p_lo; start < p_hi; start += kDmChunk) {
-    const int n_pairs = (p_hi - start < kDmChunk) ? (p_hi - start) : kDmChunk;
-    const int steps = (n_pairs + 7) >> 3, per = (steps + W - 1) / W;   // the chunk's steps, shared evenly by the warps
-    if (start != p_lo) __syncthreads();   // everyone is done with the previous chunk's indices
-    for (int i = tid; i < 8 * steps; i += kDmThreads) {
-      const bool ok = i < n_pairs;
-      s_in[i] = ok ? (in_idx ? __ldg(&in_idx[start + i]) : (int)(start + i)) : -1;
-      s_out[i] = ok ? (out_idx ? __ldg(&out_idx[start + i]) : (int)(start + i)) : -1;
-    }
-    __syncthreads();
-    const int w_end = (warp + 1) * per < steps ? (warp + 1) * per : steps;
-    for (int step = warp * per; step < w_end; step += U) {
-      float av[U][2][AF], bv[U][2][NT];
+  constexpr int STEPS = kDmChunk / (kDmThreads / 32) / 8;
+  for (int step = 0; step < STEPS; step += U) {
+    if (wbase + 8 * step >= n_pairs) break;
+    float av[U][2][AF], bv[U][2][NT];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool live = step + u < w_end;
-        const int p = 8 * (step + u);
-        const int i0 = live ? s_in[p + t] : -1, i1 = live ? s_in[p + t + 4] : -1;
-        const int o0 = live ? s_out[p + t] : -1, o1 = live ? s_out[p + t + 4] : -1;
-        dm_load<AF>(Xc + (size_t)(i0 >= 0 ? i0 : 0) * c_in, i0 >= 0, av[u][0]);
-        dm_load<AF>(Xc + (size_t)(i1 >= 0 ? i1 : 0) * c_in, i1 >= 0, av[u][1]);
-        dm_load<NT>(Dc + (size_t)(o0 >= 0 ? o0 : 0) * c_out, o0 >= 0, bv[u][0]);
-        dm_load<NT>(Dc + (size_t)(o1 >= 0 ? o1 : 0) * c_out, o1 >= 0, bv[u][1]);
+    for (int u = 0; u < U; ++u) {
+      const int p = wbase + 8 * (step + u);   // < kDmChunk: entries past n_pairs hold -1
+      const int i0 = s_in[p + t], i1 = s_in[p + t + 4], o0 = s_out[p + t], o1 = s_out[p + t + 4];
+      dm_load<AF>(Xc + (size_t)(i0 >= 0 ? i0 : 0) * c_in, i0 >= 0, av[u][0]);
+      dm_load<AF>(Xc + (size_t)(i1 >= 0 ? i1 : 0) * c_in, i1 >= 0, av[u][1]);
+      dm_load<NT>(Dc + (size_t)(o0 >= 0 ? o0 : 0) * c_out, o0 >= 0, bv[u][0]);
+      dm_load<NT>(Dc + (size_t)(o1 >= 0 ? o1 : 0) * c_out, o1 >= 0, bv[u][1]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t ahi[MT][4], alo[MT][4], bhi[NT][2], blo[NT][2];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        dm_split(av[u][0][2 * m], ahi[m][0], alo[m][0]);
+        dm_split(av[u][0][2 * m + 1], ahi[m][1], alo[m][1]);
+        dm_split(av[u][1][2 * m], ahi[m][2], alo[m][2]);
+        dm_split(av[u][1][2 * m + 1], ahi[m][3], alo[m][3]);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        uint32_t ahi[MT][4], alo[MT][4], bhi[NT][2], blo[NT][2];
+      for (int n = 0; n < NT; ++n) {
+        dm_split(bv[u][0][n], bhi[n][0], blo[n][0]);
+        dm_split(bv[u][1][n], bhi[n][1], blo[n][1]);
+      }
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          dm_split(av[u][0][2 * m], ahi[m][0], alo[m][0]);
-          dm_split(av[u][0][2 * m + 1], ahi[m][1], alo[m][1]);
-          dm_split(av[u][1][2 * m], ahi[m][2], alo[m][2]);
-          dm_split(av[u][1][2 * m + 1], ahi[m][3], alo[m][3]);
-        }
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-          dm_split(bv[u][0][n], bhi[n][0], blo[n][0]);
-          dm_split(bv[u][1][n], bhi[n][1], blo[n][1]);
+          dm_mma(accm[m][n], ahi[m], bhi[n][0], bhi[n][1]);
+          dm_corr(accc[m][n], ahi[m], alo[m], bhi[n], blo[n]);
         }
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            dm_mma(accm[m][n], ahi[m], bhi[n][0], bhi[n][1]);
-            dm_corr(accc[m][n], ahi[m], alo[m], bhi[n], blo[n]);
-          }
-      }
     }
   }
   // C fragment: c0 = C[g][2t], c1 = C[g][2t+1], c2 = C[g+8][2t], c3 = C[g+8][2t+1]  (tile channels permuted, see above)
@@ -232,9 +200,8 @@ int pgs_conv_bwd_weight_mma(const float* X, const float* dY, const int32_t* in_i
   const int nt = (c_out % 32 == 0) ? 4 : 2;
   const int mt = (c_in % 32 == 0) ? 2 : ((c_in % 48 == 0 && nt == 2) ? 3 : 1);   // 48 x 48: one X tile instead of three
   const int n_ci = c_in / (16 * mt), n_co = c_out / (8 * nt);
-  const unsigned gz = (unsigned)((max_pairs + kDmRowBlock - 1) / kDmRowBlock);   // max_pairs = rows of the output side
-  PGS_CHECK_ARG(gz <= 65535u, "too many rows for one weight-gradient launch");
-  const dim3 grid(K, n_ci * n_co, gz);
+  const unsigned gx = (unsigned)((max_pairs + kDmChunk - 1) / kDmChunk);
+  const dim3 grid(gx, n_ci * n_co, K);
   if (mt == 3)
     conv_dw_mma_kernel<3, 2><<<grid, kDmThreads, 0, s>>>(X, dY, in_idx, out_idx, offs, max_pairs, K, mirror, c_in, c_out, n_co, dW);
   else if (mt == 2 && nt == 4)

@@ -165,3 +165,4 @@ def test_backward_after_another_forward_rearranges_its_weights(cuda_device):
     ga = torch.cat([x.reshape(-1) for x in mixed]).double()
     gb = torch.cat([x.reshape(-1) for x in clean]).double()
     assert worst <= 2e-2 and 1.0 - float(torch.dot(ga, gb) / (ga.norm() * gb.norm())) <= 1e-6, worst
+
