@@ -77,12 +77,28 @@ HOST_KEYS = ("pos", "coords", "x", "batch", "y", "instance_labels", "instance_ma
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md's clocks line).  Read through NVML
+    in-process every 100 ms (two cheap calls); an `nvidia-smi -lms 50` child polling six fields perturbed the step it was
+    watching (device-resident steps 60.5 ms with it, 53.7 ms in the e2e region that runs after it is stopped).
+    PGS_BENCH_SAMPLER=smi selects the nvidia-smi loop."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.alive = [], None, None, True
+        if os.environ.get("PGS_BENCH_SAMPLER", "nvml") != "smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.nvml = pynvml
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
@@ -92,11 +108,30 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.alive:
+            try:
+                self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(get_reasons(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self.alive = False
+            sm, reasons = [], set()
+            for t, mhz, mask in self.rows:
+                if t0 <= t <= t1 + 0.3:
+                    sm.append(mhz)
+                    reasons.update(n for n, b in self.MASKS if mask & b)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -116,7 +151,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def _pin_rank_to_cores(local, world):
@@ -242,6 +277,11 @@ def run_b200(args):
         return None, clusters, None
 
     sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~1 s to come up
+    # every batch of the pool once before the W warm-up steps: the level sizes differ from batch to batch, and a batch
+    # first seen inside the timed region makes the caching allocator cudaMalloc / cudaFree multi-GB arenas there
+    # (measured: 63.7 instead of 53 ms per step when W = 3 left the fourth batch for the timed loop)
+    for i in range(SCENE_POOL):
+        step(i, False)
     for i in range(args.warmup):
         step(i, False)
     for i in range(min(args.warmup, 2)):
@@ -285,7 +325,7 @@ def run_b200(args):
             dp.step(View(d), epoch=1, step=i, batch_size=1)
             return None, tpk.region_grow(d["syn_shifted"], d["syn_pred"], d["batch"], ignore_labels=ignore, nsample=200,
                                          radius=1.5 * GRID, min_cluster_size=10), None
-        for i in range(3):
+        for i in range(max(3, len(one))):
             step1(i, False)
         ms_one, _, _ = _timed_loop(step1, args.steps, False, world, dev)
         single = {"scenes_per_gpu_per_step": 1, "ms_per_step": ms_one, "value": world * 1000.0 / ms_one, "unit": "scenes/s",
@@ -360,7 +400,8 @@ def run_b200(args):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
            "scaling": "strong" if args.config == "C4" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": dict(_cfg_workload(n, spr, args.config), l2="per-step working set (activations + gradients of 82 "
-                          "convs, neighbour tables) is several GB >> 126 MB L2; inputs rotate over %d batches" % SCENE_POOL,
+                          "convs, neighbour tables) is several GB >> 126 MB L2; inputs rotate over %d batches (each run once, untimed, "
+                          "before the W warm-up steps so that the allocator has seen every shape)" % SCENE_POOL,
                           host_cores_per_rank=cores, executor=os.environ.get("PGS_EXECUTOR", "native")),
            "e2e": {"value": scenes_per_step * 1000.0 / ms_e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d_bytes,
                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e},
