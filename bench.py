@@ -418,7 +418,7 @@ def run_b200(args):
         out["cpu_baseline"] = cpu_arm(n, steps=1, warmup=0, max_seconds=30.0, spr=spr)
         out["pq"]["cpu"] = out["cpu_baseline"]["pq_sample"]
         out["pq"]["matched"] = out["cpu_baseline"]["pq_sample"] == pq
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -541,7 +541,7 @@ def run_c3(args):
                         "tree stage, timed as one call", "achieved": alg / (hd * 1e-3) / 1e9, "peak": peak,
                         "peak_source": peak_src, "unit": "GB/s", "frac": alg / (hd * 1e-3) / 1e9 / peak, "traffic": None,
                         "numerator": "SURVEY 8d: kNN 4nD+4n, Boruvka rounds x (n(4D+8)+12n), edges 12(n-1)"}}
-    print(json.dumps(out))
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -569,7 +569,7 @@ def run_c5(args):
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": conv16[0]["frac_of_hbm_peak"],
                          "traffic": None} if conv16 else None),
            "sweep": rows, "wall_s": time.time() - t, "parity": PARITY}
-    print(json.dumps(out))
+    _emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -647,14 +647,14 @@ def run_reference(args):
     if rank != 0:
         return
     if args.config not in ("C2", "C4"):
-        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the C2 step only (config %s)" % args.config}))
+        _emit({"impl": "reference", "unavailable": "the CPU arm times the C2 step only (config %s)" % args.config})
         return
     # the same 200 k-voxel cylinder as the B200 arm; ~6-8 s per step on 16-32 host cores, so the number of measured steps
     # is bounded by time (never by shrinking the scene) and printed
     spr = 8 if args.config == "C4" else args.scenes_per_gpu
     cb = cpu_arm(args.n, steps=args.steps, warmup=0, max_seconds=150.0, spr=spr)
     ms = 1000.0 / cb["value"]
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "scenes/s",
+    _emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "scenes/s",
                       "n_gpus": args.gpus, "steps": args.steps, "steps_measured": cb["steps_measured"],
                       "warmup": 0, "ms_per_step": ms * spr,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -662,7 +662,17 @@ def run_reference(args):
                       "cpu_baseline": cb,
                       "e2e": {"value": cb["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0,
                               "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0, "parity": PARITY}))
+                      "gpu_launches": 0, "parity": PARITY})
+
+
+_OUT = None
+
+
+def _emit(obj):
+    """The bench line, on the process's original stdout (main() points descriptor 1 at stderr for everybody else)."""
+    f = _OUT if _OUT is not None else sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
 
 
 def main():
@@ -678,6 +688,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
+    # version banner there) are sent to stderr, the line itself goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
