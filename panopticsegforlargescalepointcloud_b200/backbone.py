@@ -205,9 +205,54 @@ class BaseMinkowski(nn.Module):
                 nn.init.constant_(m.bn.bias, 0)
 
     def _set_input(self, data):
-        coords = torch.cat([data.batch.unsqueeze(-1).int(), data.coords.int()], -1)
-        self.input = ME.SparseTensor(features=data.x, coordinates=coords, device=self.device)
+        pm = getattr(data, "coordinate_manager", None)
+        if isinstance(pm, PrebuiltMaps) and pm.n == data.x.shape[0]:
+            self.input = ME.SparseTensor(features=data.x.to(self.device), coordinate_manager=pm.adopt(), tensor_stride=1)
+        else:
+            coords = torch.cat([data.batch.unsqueeze(-1).int(), data.coords.int()], -1)
+            self.input = ME.SparseTensor(features=data.x, coordinates=coords, device=self.device)
         self.xyz = (data.pos if getattr(data, "pos", None) is not None else data.coords).to(self.device)
+
+    def prefetch_maps(self, batch, coords, stream=None, wait_event=None):
+        """Coordinate manager of the NEXT batch -- level-0 hash and every strided map this network will ask for, i.e.
+        the part of the forward pass that reads sizes back to the host -- built ahead of time on `stream` (default: the
+        current one), e.g. while the backward pass of the current batch runs: the read-backs then drain only `stream`.
+        `batch` int [N] and `coords` int [N,3] must be device tensors that are ready on `stream` (or after
+        `wait_event`).  Attach the returned handle to the batch as `coordinate_manager`; `forward` adopts it."""
+        cur = torch.cuda.current_stream(batch.device)
+        stream = stream or cur
+        if wait_event is not None:
+            stream.wait_event(wait_event)
+        with torch.cuda.stream(stream):
+            c4 = torch.cat([batch.unsqueeze(-1).int(), coords.int()], -1)
+            cm = ME.CoordinateManager(c4)
+            prog = fastpath.program_for(self) if fastpath.ENABLED else None
+            if prog is not None:
+                fastpath.build_strided_maps(prog, cm, 1)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return PrebuiltMaps(cm, ev, stream, c4.shape[0])
+
+
+class PrebuiltMaps:
+    """Handle returned by `prefetch_maps`: the manager, the event that marks it complete and the stream that built it."""
+
+    def __init__(self, manager, event, stream, n):
+        self.manager, self.event, self.stream, self.n = manager, event, stream, n
+
+    def adopt(self):
+        """Make the current stream wait for the build and keep the caching allocator from recycling the manager's
+        buffers (allocated on the prefetch stream) while kernels of the current stream may still read them."""
+        cm = self.manager
+        cur = torch.cuda.current_stream(cm.device)
+        if self.stream != cur:
+            cur.wait_event(self.event)
+            for m in cm.maps.values():
+                for t in (m.coords, m.tkeys, m.tvals):
+                    t.record_stream(cur)
+            for t in cm.in2out.values():
+                t.record_stream(cur)
+        return cm
 
 
 class Output:

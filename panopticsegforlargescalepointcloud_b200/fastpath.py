@@ -603,6 +603,21 @@ class _UNetFn(torch.autograd.Function):
         return (None, None, None, dX) + tuple(grads)
 
 
+def build_strided_maps(prog, cm, ts0=1):
+    """Every strided coordinate map `prog` will ask `cm` for (the part of pass 1 that reads sizes back to the host)."""
+    t = {0: ts0}
+    for kind, a, b, dst, idx, relu in prog.ops:
+        t[dst] = t[a]
+        if kind == OP_CONV:
+            mod = prog.convs[idx]
+            if mod.stride > 1:
+                if mod.TRANSPOSE:
+                    t[dst] = t[a] // mod.stride
+                else:
+                    t[dst] = t[a] * mod.stride
+                    cm.stride(t[a], t[dst])
+
+
 def program_for(net):
     """Compiled tape of `net` (cached on the module), or None when its structure is not supported."""
     prog = net.__dict__.get("_pgs_program", False)

@@ -281,8 +281,17 @@ class _PanopticBase(BaseModel):
         CPU; here one device-resident batch feeds backbone, clustering, scoring and losses)."""
         keys = ["pos", "coords", "x", "batch"] + self.__REQUIRED_LABELS__
         self.input = _Batch(**{k: _get(data, k).to(device, non_blocking=True) for k in keys})
+        pm = getattr(data, "coordinate_manager", None)     # handle from prefetch_maps (backbone.PrebuiltMaps), optional
+        if pm is not None:
+            self.input.coordinate_manager = pm
         self.raw_pos = self.input.pos
         self.labels = PanopticLabels(**{l: self.input[l] for l in self.__REQUIRED_LABELS__})
+
+    def prefetch_maps(self, data, stream=None, wait_event=None):
+        """Coordinate maps of the NEXT batch built ahead of time (backbone.BaseMinkowski.prefetch_maps): call it with the
+        device-resident batch after the current step has been launched, attach the result to that batch as
+        `coordinate_manager` before `set_input`.  The forward pass then has no host read-back left."""
+        return self.Backbone.prefetch_maps(_get(data, "batch"), _get(data, "coords"), stream=stream, wait_event=wait_event)
 
     # ---- clustering recipes ----
     def _region_grow(self, pos, predicted_labels, nsample=None):

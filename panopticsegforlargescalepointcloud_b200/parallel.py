@@ -113,6 +113,10 @@ class DataParallelStep:
         else:
             self.bucket.all_reduce_mean()
 
+    def prefetch(self, data, stream=None, wait_event=None):
+        """Build the next batch's coordinate maps while the current step runs (panoptic `prefetch_maps`)."""
+        return self.model.prefetch_maps(data, stream=stream, wait_event=wait_event)
+
     def step(self, data, epoch, step=0, batch_size=1):
         self.model.set_input(data, self.model.device)
         self.model.optimize_parameters2(epoch, step, batch_size)

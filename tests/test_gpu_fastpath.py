@@ -166,3 +166,42 @@ def test_backward_after_another_forward_rearranges_its_weights(cuda_device):
     gb = torch.cat([x.reshape(-1) for x in clean]).double()
     assert worst <= 2e-2 and 1.0 - float(torch.dot(ga, gb) / (ga.norm() * gb.norm())) <= 1e-6, worst
 
+
+
+def test_prefetched_coordinate_maps_are_adopted(cuda_device):
+    """backbone.prefetch_maps on a second stream: the forward pass adopts the prebuilt manager (no map is rebuilt) and
+    gives the same output and gradients as the inline build."""
+    from panopticsegforlargescalepointcloud_b200 import backbone as bb, me
+    torch.manual_seed(3)
+    net = bb.Minkowski("unet", input_nc=4, config=bb.paper_backbone_config(16)).to(cuda_device)
+    net.train(False)
+    rng = np.random.default_rng(12)
+    coords = _scene(4, n=9000, extent=48)
+    x = rng.standard_normal((len(coords), 4)).astype(np.float32)
+    g = torch.from_numpy(rng.standard_normal((len(coords), 16)).astype(np.float32)).to(cuda_device)
+    out0, dx0, g0 = _run(net, coords, x, g, cuda_device, False)
+
+    side = torch.cuda.Stream(device=cuda_device)
+    xin = _batch(coords, x, cuda_device)
+    torch.cuda.synchronize()
+    pm = net.prefetch_maps(xin.batch, xin.coords, stream=side)
+    assert sorted(pm.manager.maps) == [1, 2, 4, 8, 16, 32, 64] and pm.n == len(coords)
+    xin.coordinate_manager = pm
+    built = []
+    orig = me.build_coordinate_map
+    try:
+        me.build_coordinate_map = lambda *a, **k: (built.append(1), orig(*a, **k))[1]
+        for p in net.parameters():
+            p.grad = None
+        xin.x.requires_grad_(True)
+        out1 = net(xin).x
+        out1.backward(g)
+    finally:
+        me.build_coordinate_map = orig
+    assert not built, "the forward pass rebuilt a coordinate map although a prebuilt manager was attached"
+    assert net.input.coordinate_manager is pm.manager
+
+    def close(a, b, tol):
+        return float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-6)
+
+    assert close(out1.detach(), out0, 2e-5) and close(xin.x.grad, dx0, 5e-3)
