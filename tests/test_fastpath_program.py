@@ -123,3 +123,22 @@ def test_native_executor_records_match_the_header():
     rc = lib.pgs_unet_forward(bad.ctypes.data, len(bad), p.n_slots, ptrs.ctypes.data, sn.ctypes.data, sc.ctypes.data,
                               None, None, None, None, None, None)
     assert rc != 0 and b"slot out of range" in lib.pgs_last_error()
+
+
+def test_strided_maps_requested_ahead_of_the_forward_pass():
+    """fastpath.build_strided_maps (used by backbone.prefetch_maps): the down path asks for each doubling once, in
+    order; the transposed convolutions of the up path reuse the encoder's maps and ask for nothing."""
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def stride(self, ts_in, ts_out):
+            self.calls.append((ts_in, ts_out))
+
+    rec = Recorder()
+    fastpath.build_strided_maps(fastpath.Program(bb.Minkowski("unet", input_nc=4, config=bb.paper_backbone_config(16))), rec, 1)
+    assert rec.calls == [(1, 2), (2, 4), (4, 8), (8, 16), (16, 32), (32, 64)]
+    rec = Recorder()
+    fastpath.build_strided_maps(fastpath.Program(bb.Minkowski("unet", input_nc=4, config=bb.two_level_config(16))), rec, 1)
+    assert rec.calls == [(1, 2)]
+
