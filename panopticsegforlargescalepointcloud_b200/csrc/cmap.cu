@@ -208,7 +208,6 @@ using namespace pgs;
 
 extern "C" {
 
-
 int64_t pgs_cmap_capacity(int64_t n) {
   int64_t cap = 1024;
   while (cap < 2 * n) cap <<= 1;
